@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- the FlatSparray hot path on B200 (one process per GPU).
+
+A "step" is one pass of the hot path over one batch of synthetic input: BASELINE.json
+config[1] -- two random (256,256,256,64) float32 operands at 1% density (~10.7 M nnz
+each, 256 MB of operands: larger than L2, so nothing is re-used between steps) --
+``c = a * b`` (intersection merge, flat.py:424-434) followed by ``c.sum(axis=2)``
+(flat.py:607-626).  metric = binop-merge throughput in input nnz per second.
+
+  value      : whole-job Gnnz/s with operands resident in HBM (CUDA events, max over ranks)
+  e2e        : same metric through the public FlatSparray API starting from pinned HOST
+               buffers (H2D of all four operand arrays and D2H of the result inside the
+               timed region)
+  roofline   : the dominant kernel (fused merge-path intersection) timed alone with CUDA
+               events on its launch stream; algorithmic bytes / time vs the measured HBM peak
+  cpu_baseline / --impl reference : the reference's CPU path (its own Cython merge kernel
+               from oracle/_ref when built, else the C port, + the numpy glue of flat.py
+               restated in oracle/) timed on this box's host cores (single-threaded: the
+               reference has no threading)
+
+N > 1: weak scaling.  The array is range-partitioned on its flat index (contiguous
+blocks of axis 0), rank r owns an equally sized shard; co-partitioned ``a*b`` and the
+axis-2 sum need no collective, so ranks only meet at the barriers.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+SHAPE = (256, 256, 256, 64)
+DENSITY = 0.01
+DTYPE = np.float32
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def load_oracle():
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import flat_oracle as fo
+    import build_ref
+    ref = build_ref.load()          # the reference's own Cython kernel, if it was built
+    return fo, ref
+
+
+def hbm_peak():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def gen_operands(rank):
+    """SURVEY.md section 8(d) generator; seeds a=1, b=2 (offset per rank for the sharded runs)."""
+    fo, _ = load_oracle()
+    ai, av = fo.random_operand(SHAPE, DENSITY, DTYPE, 1 + 100 * rank)
+    bi, bv = fo.random_operand(SHAPE, DENSITY, DTYPE, 2 + 100 * rank)
+    return ai, av, bi, bv
+
+
+def cpu_step(fo, ref, ai, av, bi, bv):
+    """The reference's CPU path for one step: flat.py:424-434 then flat.py:607-626."""
+    if ref is not None:
+        ci, la, lb = ref.intersect1d_sorted(ai, bi, return_inds=True)      # the reference's Cython kernel
+        ci, cv = np.asarray(ci), np.multiply(av[la], bv[lb])
+    else:
+        ci, cv = fo.pairwise_intersect(ai, av, bi, bv, np.multiply)        # C port
+    return fo.sum_axis(ci, cv, SHAPE, 2)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    fo, ref = load_oracle()
+    ai, av, bi, bv = gen_operands(0)
+    for _ in range(args.warmup):
+        cpu_step(fo, ref, ai, av, bi, bv)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(fo, ref, ai, av, bi, bv)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = (len(ai) + len(bi)) / dt / 1e9
+    kind = "reference" if ref is not None else "port"
+    sample = ("full config[1] step (%d + %d nnz) per step; merge kernel = %s; numpy glue restated in oracle/flat_oracle.py"
+              % (len(ai), len(bi), "the reference's _merge.pyx compiled into oracle/_ref" if ref is not None
+                 else "C port oracle/merge_oracle.c"))
+    print(json.dumps({
+        "impl": "reference", "metric": "FlatSparray binop merge throughput (a*b then sum(axis=2))",
+        "value": val, "unit": "Gnnz/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE config[1]: (256,256,256,64) float32, 1% density, a*b then sum(axis=2)",
+                   "nnz_a": len(ai), "nnz_b": len(bi)},
+        "cpu_baseline": {"value": val, "unit": "Gnnz/s", "cores": 1, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "Gnnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-ops", action="store_true", help="skip the per-op breakdown (other configs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: sparray_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import sparray_b200 as sp
+    from sparray_b200 import _dtypes as dt
+    from sparray_b200._lib import check, lib, ptr, stream, workspace
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ai, av, bi, bv = gen_operands(rank)
+    na, nb = len(ai), len(bi)
+    host = [torch.from_numpy(x).pin_memory() for x in (ai, av, bi, bv)]
+    A = sp.FlatSparray(host[0].cuda(), host[1].cuda(), shape=SHAPE, is_canonical=True)
+    B = sp.FlatSparray(host[2].cuda(), host[3].cuda(), shape=SHAPE, is_canonical=True)
+
+    def step():
+        c = A * B
+        return c, c.sum(axis=2)
+
+    # ---- value: operands resident in HBM -------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.spb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        c, s = step()
+    e1.record()
+    barrier()
+    launches = lib.spb_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    value = world * (na + nb) / (ms_step * 1e-3) / 1e9
+    nout = c.nnz
+
+    # ---- e2e: pinned host buffers -> public API -> host result -----------------------------------
+    def e2e_step():
+        a = sp.FlatSparray(host[0].cuda(non_blocking=True), host[1].cuda(non_blocking=True), shape=SHAPE,
+                           is_canonical=True)
+        b = sp.FlatSparray(host[2].cuda(non_blocking=True), host[3].cuda(non_blocking=True), shape=SHAPE,
+                           is_canonical=True)
+        r = (a * b).sum(axis=2)
+        return r.indices.cpu(), r.data.cpu()
+    for _ in range(3):
+        ri, rd = e2e_step()
+    e2e_steps = max(3, min(args.steps, 20))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ri, rd = e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) / e2e_steps * 1e3)
+    barrier()
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    d2h = ri.numel() * 8 + rd.numel() * 8
+    e2e_value = world * (na + nb) / (e2e_ms * 1e-3) / 1e9
+
+    # ---- roofline: the fused intersection kernel alone, CUDA events on its launch stream -----------
+    cap = min(na, nb)
+    out_idx = torch.empty(cap, dtype=torch.int64, device="cuda")
+    out_val = torch.empty(cap, dtype=torch.float32, device="cuda")
+    cnt = torch.empty(1, dtype=torch.int64, device="cuda")
+
+    def launch_intersect():
+        check(lib.spb_intersect_binop(dt.BINOPS["mul"], dt.SPB_F32, ptr(A.indices), ptr(A.data), na, ptr(B.indices),
+                                      ptr(B.data), nb, ptr(out_idx), ptr(out_val), ptr(cnt), workspace(), stream()))
+    for _ in range(5):
+        launch_intersect()
+    reps = 50
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    torch.cuda.synchronize()
+    for a_, b_ in evs:
+        a_.record()
+        launch_intersect()
+        b_.record()
+    torch.cuda.synchronize()
+    k_ms = float(np.mean([a_.elapsed_time(b_) for a_, b_ in evs]))
+    alg_bytes = (na + nb) * 8 + nout * (4 + 4) + nout * (8 + 4)
+    peak, peak_src = hbm_peak()
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "setop_kernel<float,float,INTERSECT> (spb_intersect_binop)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "peak_source": peak_src,
+                "timing": "CUDA events around each of %d launches on the launch stream; 256 MB of operands > 126 MB L2" % reps}
+
+    # ---- per-op breakdown at the other BASELINE configs (N=1 only; not the headline) ---------------
+    ops = None
+    if world == 1 and not args.no_ops:
+        ops = op_breakdown(sp, torch, A, B, peak)
+
+    # ---- CPU baseline beside it (rank 0, N=1) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1:
+        fo, ref = load_oracle()
+        best = 1e30
+        for _ in range(3):
+            t0 = time.perf_counter()
+            cpu_step(fo, ref, ai, av, bi, bv)
+            best = min(best, time.perf_counter() - t0)
+        cpu = {"value": (na + nb) / best / 1e9, "unit": "Gnnz/s", "cores": 1,
+               "kind": "reference" if ref is not None else "port", "ms_per_step": best * 1e3,
+               "host_cores_available": os.cpu_count(),
+               "sample": "the full step (whole workload, best of 3): %s merge kernel + numpy glue of flat.py restated in "
+                         "oracle/flat_oracle.py; single-threaded like the reference"
+                         % ("the reference's Cython (oracle/_ref)" if ref is not None else "C-port")}
+
+    if rank == 0:
+        out = {
+            "metric": "FlatSparray binop merge throughput (a*b then sum(axis=2))",
+            "value": value, "unit": "Gnnz/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config[1]: (256,256,256,64) float32, 1% density, c=a*b (intersection) "
+                                   "then c.sum(axis=2)", "nnz_a": na, "nnz_b": nb, "nnz_out": nout,
+                       "per_gpu_shard": "one config[1]-sized range shard per GPU, co-partitioned (no collective)",
+                       "l2": "operands (256 MB per GPU) exceed the 126 MB L2; no flush needed"},
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "Gnnz/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if ops is not None:
+            out["ops"] = ops
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_op(torch, fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def synth_sorted(torch, n, size, dtype, seed):
+    """Sorted duplicate-free flat indices of ~uniform density generated on the device (for
+    configs too large to build on the host): cumulative sum of random positive gaps."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    gap = max(int(size // n), 1)
+    steps = torch.randint(1, 2 * gap, (n,), device="cuda", generator=g, dtype=torch.int64) if gap > 1 else \
+        torch.ones(n, device="cuda", dtype=torch.int64)
+    idx = torch.cumsum(steps, 0) - 1
+    idx = idx[idx < size]
+    val = torch.randn(idx.numel(), device="cuda", generator=g, dtype=dtype)
+    return idx.contiguous(), val
+
+
+def op_breakdown(sp, torch, A, B, peak):
+    """API-level timings (count read-back included) at the other BASELINE configs."""
+    res = {}
+
+    def rec(name, n_in, alg_bytes, fn, reps=10):
+        med, best = time_op(torch, fn, reps=reps)
+        res[name] = {"ms": med, "ms_best": best, "Gnnz_per_s": n_in / (med * 1e-3) / 1e9,
+                     "alg_GBps": alg_bytes / (med * 1e-3) / 1e9, "frac_of_hbm_peak": alg_bytes / (med * 1e-3) / 1e9 / peak}
+    na, nb = A.nnz, B.nnz
+    u = A + B
+    rec("c2_union_a+b_f32", na + nb, (na + nb + u.nnz) * 12, lambda: A + B)
+    c = A * B
+    rec("c2_intersect_a*b_f32", na + nb, (na + nb) * 8 + c.nnz * 8 + c.nnz * 12, lambda: A * B)
+    s = A.sum(axis=2)
+    rec("c2_sum_axis2_full_operand", na, na * 12 + s.nnz * 16, lambda: A.sum(axis=2))
+    s = A.sum(axis=3)
+    rec("c2_sum_axis3_last_axis", na, na * 12 + s.nnz * 16, lambda: A.sum(axis=3))
+    rec("c2_transpose_3210", na, 2 * na * 12, lambda: A.transpose(3, 2, 1, 0))
+    del u, c, s
+    # config[0]: 10000 x 10000 float64 at 1%
+    n1 = 1_000_000
+    i1, v1 = synth_sorted(torch, n1, 10 ** 8, torch.float64, 1)
+    i2, v2 = synth_sorted(torch, n1, 10 ** 8, torch.float64, 2)
+    X = sp.FlatSparray(i1, v1, shape=(10000, 10000), is_canonical=True)
+    Y = sp.FlatSparray(i2, v2, shape=(10000, 10000), is_canonical=True)
+    u = X + Y
+    rec("c1_union_a+b_f64", X.nnz + Y.nnz, (X.nnz + Y.nnz + u.nnz) * 16, lambda: X + Y, reps=20)
+    rec("c1_intersect_a*b_f64", X.nnz + Y.nnz, (X.nnz + Y.nnz) * 8, lambda: X * Y, reps=20)
+    # config[2] literal: (4096,4096,1024) float32 at 1e-4 -> 1.7 M nnz, swapaxes(0,2)
+    i3, v3 = synth_sorted(torch, 1_717_987, 2 ** 34, torch.float32, 3)
+    Z = sp.FlatSparray(i3, v3, shape=(4096, 4096, 1024), is_canonical=True)
+    rec("c3_literal_swapaxes02_f32", Z.nnz, 2 * Z.nnz * 12, lambda: Z.swapaxes(0, 2))
+    # config[3]: 1M x 1M float64, 100 M nnz: SpMV and sum(axis=1)
+    i4, v4 = synth_sorted(torch, 100_000_000, 10 ** 12, torch.float64, 4)
+    W = sp.FlatSparray(i4, v4, shape=(10 ** 6, 10 ** 6), is_canonical=True)
+    x = torch.randn(10 ** 6, device="cuda", dtype=torch.float64)
+    from sparray_b200 import _kernels as k
+    rec("c4_spmv_f64_100M", W.nnz, W.nnz * 16 + 2 * 8 * 10 ** 6, lambda: k.spmv(W.indices, W.data, 10 ** 6, 10 ** 6, x, torch.float64), reps=5)
+    s = W.sum(axis=1)
+    rec("c4_sum_axis1_f64_100M", W.nnz, W.nnz * 16 + s.nnz * 16, lambda: W.sum(axis=1), reps=5)
+    rec("c4_transpose_f64_100M", W.nnz, 2 * W.nnz * 16, lambda: W.T, reps=3)
+    return res
+
+
+if __name__ == "__main__":
+    main()

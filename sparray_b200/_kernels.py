@@ -1,0 +1,325 @@
+"""Thin Python wrappers: allocate outputs as torch tensors (device memory and
+streams are torch's job), call the C ABI (include/sparray_b200.h), trim to the
+device-side count.  No arithmetic happens in Python or in torch ops here."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _dtypes as dt
+from ._lib import check, lib, ptr, require_cuda, stream, workspace
+
+
+def _empty(n, dtype, like):
+    return torch.empty(int(n), dtype=dtype, device=like.device)
+
+
+def _count(t):
+    """Read a device int64 count (the one host sync of an op with a data-dependent size)."""
+    return int(t.item())
+
+
+def _i64c(t, name):
+    """The seam's calling convention: int64, C-contiguous."""
+    if t.dtype != torch.int64:
+        raise ValueError("Buffer dtype mismatch for %s, expected int64 but got %s" % (name, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s is not C-contiguous" % name)
+    return t
+
+
+# ---- section 1: the compat seam -------------------------------------------------------------
+
+def union1d_sorted(a, b, return_masks=False):
+    require_cuda()
+    a, b = _i64c(a, "a"), _i64c(b, "b")
+    na, nb = a.numel(), b.numel()
+    out = _empty(na + nb, torch.int64, a)
+    cnt = _empty(1, torch.int64, a)
+    lut = a_only = b_only = None
+    if return_masks:
+        lut = _empty(na + nb, torch.uint8, a)
+        a_only = _empty(na, torch.bool, a)
+        b_only = _empty(nb, torch.bool, a)
+    check(lib.spb_union1d_sorted(ptr(a), na, ptr(b), nb, ptr(out), ptr(lut), ptr(a_only), ptr(b_only),
+                                 ptr(cnt), workspace(), stream()))
+    n = _count(cnt)
+    if not return_masks:
+        return out[:n]
+    return out[:n], lut[:n], a_only, b_only
+
+
+def intersect1d_sorted(a, b, return_inds=False):
+    require_cuda()
+    a, b = _i64c(a, "a"), _i64c(b, "b")
+    na, nb = a.numel(), b.numel()
+    m = min(na, nb)
+    out = _empty(m, torch.int64, a)
+    cnt = _empty(1, torch.int64, a)
+    ai = bi = None
+    if return_inds:
+        ai = _empty(m, torch.int64, a)
+        bi = _empty(m, torch.int64, a)
+    check(lib.spb_intersect1d_sorted(ptr(a), na, ptr(b), nb, ptr(out), ptr(ai), ptr(bi), ptr(cnt),
+                                     workspace(), stream()))
+    n = _count(cnt)
+    if not return_inds:
+        return out[:n]
+    return out[:n], ai[:n], bi[:n]
+
+
+def combine_ranges(ranges, shape, result_size, inner=False, device=None):
+    require_cuda()
+    ranges = np.ascontiguousarray(ranges, dtype=np.int64)
+    shape_arr = np.ascontiguousarray(shape, dtype=np.int64)
+    if ranges.ndim != 2 or ranges.shape[1] != 3 or ranges.shape[0] != len(shape_arr):
+        raise ValueError("ranges must have shape (ndim, 3)")
+    out = torch.empty(int(result_size), dtype=torch.int64, device=device or "cuda")
+    check(lib.spb_combine_ranges(ranges.ctypes.data_as(ctypes.c_void_p), shape_arr.ctypes.data_as(ctypes.c_void_p),
+                                 len(shape_arr), ptr(out), int(result_size), int(bool(inner)), stream()))
+    return out
+
+
+def len_range(start, stop, step):
+    return int(lib.spb_len_range(int(start), int(stop), int(step)))
+
+
+# ---- section 2: fused sparse (op) sparse ----------------------------------------------------
+
+def setop_binop(kind, op, a_idx, a_val, b_idx, b_val):
+    """kind: 'union' | 'intersect'.  Values must already share a dtype."""
+    require_cuda()
+    assert a_val.dtype == b_val.dtype
+    na, nb = a_idx.numel(), b_idx.numel()
+    cap = na + nb if kind == "union" else min(na, nb)
+    out_dtype = torch.bool if op in dt.COMPARISONS else a_val.dtype
+    out_idx = _empty(cap, torch.int64, a_idx)
+    out_val = _empty(cap, out_dtype, a_idx)
+    cnt = _empty(1, torch.int64, a_idx)
+    fn = lib.spb_union_binop if kind == "union" else lib.spb_intersect_binop
+    check(fn(dt.BINOPS[op], dt.spb_dtype(a_val.dtype), ptr(a_idx), ptr(a_val), na, ptr(b_idx), ptr(b_val), nb,
+             ptr(out_idx), ptr(out_val), ptr(cnt), workspace(), stream()))
+    n = _count(cnt)
+    return out_idx[:n], out_val[:n]
+
+
+# ---- section 3: maps, conversion, lookup -----------------------------------------------------
+
+def unary_map(op, data, scalar=0):
+    require_cuda()
+    out_dtype = torch.bool if op.endswith("_s") and op[:2] in ("lt", "le", "gt", "ge", "eq", "ne") else data.dtype
+    out = torch.empty_like(data, dtype=out_dtype)
+    is_float = data.dtype.is_floating_point
+    check(lib.spb_unary_map(dt.UNOPS[op], dt.spb_dtype(data.dtype), ptr(data), ptr(out), data.numel(),
+                            float(scalar) if is_float else 0.0, 0 if is_float else int(scalar), stream()))
+    return out
+
+
+def cast(data, dtype):
+    require_cuda()
+    if data.dtype == dtype:
+        return data.clone()          # device-to-device memcpy
+    out = torch.empty_like(data, dtype=dtype)
+    check(lib.spb_cast(dt.spb_dtype(data.dtype), dt.spb_dtype(dtype), ptr(data), ptr(out), data.numel(), stream()))
+    return out
+
+
+def scatter_dense(idx, val, size):
+    require_cuda()
+    dense = torch.zeros(int(size), dtype=val.dtype, device=val.device)   # cudaMemset: plumbing
+    check(lib.spb_scatter_dense(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), idx.numel(), ptr(dense), stream()))
+    return dense
+
+
+def gather(src, pos):
+    require_cuda()
+    out = torch.empty(pos.numel(), dtype=src.dtype, device=src.device)
+    check(lib.spb_gather(dt.spb_dtype(src.dtype), ptr(src), ptr(pos), pos.numel(), ptr(out), stream()))
+    return out
+
+
+def lower_bound(sorted_idx, query, want_found=True):
+    require_cuda()
+    pos = torch.empty(query.numel(), dtype=torch.int64, device=query.device)
+    found = torch.empty(query.numel(), dtype=torch.bool, device=query.device) if want_found else None
+    check(lib.spb_lower_bound(ptr(sorted_idx), sorted_idx.numel(), ptr(query), query.numel(), ptr(pos), ptr(found),
+                              stream()))
+    return pos, found
+
+
+def select_nonzero(dense_flat):
+    require_cuda()
+    n = dense_flat.numel()
+    idx = torch.empty(n, dtype=torch.int64, device=dense_flat.device)
+    val = torch.empty(n, dtype=dense_flat.dtype, device=dense_flat.device)
+    cnt = torch.empty(1, dtype=torch.int64, device=dense_flat.device)
+    check(lib.spb_select_nonzero(dt.spb_dtype(dense_flat.dtype), ptr(dense_flat), n, ptr(idx), ptr(val), ptr(cnt),
+                                 workspace(), stream()))
+    k = _count(cnt)
+    return idx[:k].clone(), val[:k].clone()
+
+
+def sum_all(data):
+    """Returns a python float (float dtypes, float64 accumulate) or int."""
+    require_cuda()
+    is_float = data.dtype.is_floating_point
+    out = torch.empty(1, dtype=torch.float64 if is_float else torch.int64, device=data.device)
+    check(lib.spb_sum_all(dt.spb_dtype(data.dtype), ptr(data), data.numel(), ptr(out), workspace(), stream()))
+    return out.item()
+
+
+def select_pairs(idx, val, keep):
+    require_cuda()
+    n = idx.numel()
+    out_idx = torch.empty(n, dtype=torch.int64, device=idx.device)
+    out_val = torch.empty(n, dtype=val.dtype, device=idx.device)
+    cnt = torch.empty(1, dtype=torch.int64, device=idx.device)
+    check(lib.spb_select_flagged(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), ptr(keep), n, ptr(out_idx),
+                                 ptr(out_val), ptr(cnt), workspace(), stream()))
+    k = _count(cnt)
+    return out_idx[:k], out_val[:k]
+
+
+def min_max(data, which):
+    require_cuda()
+    if data.numel() == 0:
+        raise ValueError("zero-size array to reduction operation %s which has no identity" % which)
+    out = torch.empty(1, dtype=data.dtype, device=data.device)
+    check(lib.spb_min_max(dt.spb_dtype(data.dtype), ptr(data), data.numel(), int(which == "max"), ptr(out),
+                          workspace(), stream()))
+    return out.cpu().numpy()[0]
+
+
+# ---- section 4: reductions over sorted keys ---------------------------------------------------
+
+def reduce_by_key(keys, vals, divisor=1):
+    """Sorted keys -> (unique keys // divisor, float64 sums)."""
+    require_cuda()
+    n = keys.numel()
+    out_keys = torch.empty(n, dtype=torch.int64, device=keys.device)
+    out_sums = torch.empty(n, dtype=torch.float64, device=keys.device)
+    cnt = torch.empty(1, dtype=torch.int64, device=keys.device)
+    check(lib.spb_reduce_by_key(dt.spb_dtype(vals.dtype), ptr(keys), ptr(vals), n, int(divisor), ptr(out_keys),
+                                ptr(out_sums), ptr(cnt), workspace(), stream()))
+    k = _count(cnt)
+    return out_keys[:k], out_sums[:k]
+
+
+def spmv(idx, val, ncols, nrows, x, vdtype):
+    """Dense y (dtype vdtype) = A @ x for A given by sorted flat indices."""
+    require_cuda()
+    if vdtype not in (torch.float32, torch.float64):
+        vdtype = torch.float64
+    if val.dtype != vdtype:
+        val = cast(val, vdtype)
+    if x.dtype != vdtype:
+        x = cast(x, vdtype)
+    y = torch.empty(int(nrows), dtype=torch.float64, device=idx.device)
+    check(lib.spb_spmv(dt.spb_dtype(vdtype), ptr(idx), ptr(val), idx.numel(), int(ncols), int(nrows), ptr(x), ptr(y),
+                       workspace(), stream()))
+    return y if vdtype == torch.float64 else cast(y, vdtype)
+
+
+# ---- section 5: re-key + radix sort ------------------------------------------------------------
+
+def rekey_sort(idx, val, in_strides, out_strides, sort_divisor, sort_bits):
+    """(new keys sorted, values permuted alike); inputs untouched."""
+    require_cuda()
+    from . import _plan
+    n = idx.numel()
+    out_idx = torch.empty_like(idx)
+    out_val = torch.empty_like(val) if val is not None else None
+    need_tmp = sort_bits > 8
+    tmp_idx = torch.empty_like(idx) if need_tmp else None
+    tmp_val = torch.empty_like(val) if (need_tmp and val is not None) else None
+    ndim = len(in_strides)
+    ins = (ctypes.c_int64 * max(ndim, 1))(*in_strides)
+    outs = (ctypes.c_int64 * max(ndim, 1))(*out_strides)
+    check(lib.spb_rekey_sort(dt.spb_dtype(val.dtype) if val is not None else dt.SPB_I64, ptr(idx), ptr(val), n, ndim,
+                             ctypes.cast(ins, ctypes.c_void_p), ctypes.cast(outs, ctypes.c_void_p),
+                             int(sort_divisor), int(sort_bits), ptr(out_idx), ptr(out_val), ptr(tmp_idx),
+                             ptr(tmp_val), workspace(), stream()))
+    return out_idx, out_val
+
+
+def transpose(idx, val, shape, axes):
+    from . import _plan
+    in_s, out_s, div, bits = _plan.transpose_plan(shape, axes)
+    return rekey_sort(idx, val, in_s, out_s, div, bits)
+
+
+def sum_axis(idx, val, shape, axis):
+    """(new sorted unique flat indices, float64 sums) -- flat.py:617-625."""
+    from . import _plan
+    plan = _plan.axis_sum_plan(shape, axis)
+    if plan[0] == "last":
+        return reduce_by_key(idx, val, plan[1])
+    _, in_s, out_s, bits = plan
+    keys, vals = rekey_sort(idx, val, in_s, out_s, 1, bits)
+    return reduce_by_key(keys, vals, 1)
+
+
+def canonicalize(idx, val, max_key=None):
+    """Sort by index and sum duplicates in float64, cast back (flat.py:32-35)."""
+    if idx.numel() == 0:
+        return idx, val
+    if max_key is None:
+        max_key = int(min_max(idx, "max"))
+        if int(min_max(idx, "min")) < 0:
+            raise ValueError("negative flat index")
+    bits = max(int(max_key), 1).bit_length()
+    keys, vals = rekey_sort(idx, val, [], [], 1, bits)
+    out_idx, sums = reduce_by_key(keys, vals, 1)
+    return out_idx, cast(sums, val.dtype)
+
+
+# ---- section 6: __getitem__ ------------------------------------------------------------------------
+
+def getitem_box(idx, val, shape, ranges, new_shape):
+    """ints + slices: one pass over the stored elements inside the box's flat-index span."""
+    require_cuda()
+    ranges = np.ascontiguousarray(ranges, dtype=np.int64)
+    shape_arr = np.ascontiguousarray(shape, dtype=np.int64)
+    strides = np.ones(len(shape), dtype=object)
+    for ax in range(len(shape) - 2, -1, -1):
+        strides[ax] = strides[ax + 1] * int(shape[ax + 1])
+    lens = [len_range(*r) for r in ranges]
+    lo_flat = sum(int(r[0]) * int(s) for r, s in zip(ranges, strides))
+    hi_flat = sum((int(r[0]) + (l - 1) * int(r[2])) * int(s) for r, l, s in zip(ranges, lens, strides))
+    # restrict the scan to the stored elements in [lo_flat, hi_flat]: two binary searches
+    q = torch.tensor([lo_flat, hi_flat + 1], dtype=torch.int64, device=idx.device)
+    pos, _ = lower_bound(idx, q, want_found=False)
+    lo, hi = (int(x) for x in pos.cpu().tolist())
+    sub_idx, sub_val = idx[lo:hi], val[lo:hi]
+    n = hi - lo
+    out_idx = torch.empty(n, dtype=torch.int64, device=idx.device)
+    out_val = torch.empty(n, dtype=val.dtype, device=idx.device)
+    cnt = torch.empty(1, dtype=torch.int64, device=idx.device)
+    check(lib.spb_getitem_box(dt.spb_dtype(val.dtype), ptr(sub_idx), ptr(sub_val), n, len(shape),
+                              shape_arr.ctypes.data_as(ctypes.c_void_p), ranges.ctypes.data_as(ctypes.c_void_p),
+                              ptr(out_idx), ptr(out_val), ptr(cnt), workspace(), stream()))
+    k = _count(cnt)
+    return out_idx[:k].clone(), out_val[:k].clone()
+
+
+def outer_sum(offsets, new_shape, device):
+    """Flat query of a mixed slice/array index: outer sum of per-axis offset lists."""
+    require_cuda()
+    lens = np.asarray([len(o) for o in offsets], dtype=np.int64)
+    cat = torch.from_numpy(np.concatenate([np.asarray(o, dtype=np.int64) for o in offsets])).to(device)
+    n = int(np.prod(lens, dtype=object))
+    out = torch.empty(n, dtype=torch.int64, device=device)
+    check(lib.spb_outer_sum(ptr(cat), len(offsets), lens.ctypes.data_as(ctypes.c_void_p), ptr(out), n, stream()))
+    return out
+
+
+def lookup_compact(sorted_idx, val, query):
+    require_cuda()
+    nq = query.numel()
+    out_idx = torch.empty(nq, dtype=torch.int64, device=query.device)
+    out_val = torch.empty(nq, dtype=val.dtype, device=query.device)
+    cnt = torch.empty(1, dtype=torch.int64, device=query.device)
+    check(lib.spb_lookup_compact(dt.spb_dtype(val.dtype), ptr(sorted_idx), ptr(val), sorted_idx.numel(), ptr(query),
+                                 nq, ptr(out_idx), ptr(out_val), ptr(cnt), workspace(), stream()))
+    k = _count(cnt)
+    return out_idx[:k].clone(), out_val[:k].clone()

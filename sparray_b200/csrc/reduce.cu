@@ -1,0 +1,480 @@
+// sparray_b200/csrc/reduce.cu -- segmented reduction over sorted keys.
+//
+//   * spb_reduce_by_key : group-by-key float64 sum over an already sorted key
+//     stream -- the np.unique + np.bincount of FlatSparray.sum(axis) (flat.py:620-625)
+//     and of the non-canonical ctor (flat.py:34-35).  The segment key is
+//     idx / divisor, so sum(axis=last) needs no re-keyed copy of the indices.
+//   * spb_spmv          : y[row] = sum val * x[col] with row = idx / ncols -- the
+//     O(nnz) form of a.dot(x) (flat.py:538-568).
+//   * spb_min_max, spb_select_flagged.
+//
+// One pass, one launch: coalesced loads -> padded shared-memory transpose ->
+// thread-sequential segmented scan -> block scan -> decoupled look-back that
+// carries (number of segment heads, open-segment partial sum) across tiles.
+#include "common.cuh"
+
+namespace spb {
+
+constexpr int kRNT = 256;
+constexpr int kRVT = 8;
+constexpr int kRTile = kRNT * kRVT;
+
+// look-back word: [63:62] status, [61:48] epoch, [47] tile contains a head, [46:0] head count
+constexpr uint64_t kHeadFlag = 1ull << 47;
+constexpr uint64_t kHeadCountMask = (1ull << 47) - 1;
+
+__device__ __forceinline__ void st_release(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_cg_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct Carry {       // (heads, open partial sum, any head) -- the scan operand
+    int64_t heads;
+    double val;
+    bool flag;
+};
+// a then b (a older): heads add; the open sum restarts at b's last head
+__device__ __forceinline__ Carry combine(const Carry& a, const Carry& b) {
+    Carry r;
+    r.heads = a.heads + b.heads;
+    r.val = b.flag ? b.val : a.val + b.val;
+    r.flag = a.flag || b.flag;
+    return r;
+}
+
+struct ReduceParams {
+    const int64_t* keys;
+    const void* vals;
+    int64_t n;
+    FastDiv div;            // segment key = keys[i] / div.d
+    const void* x;          // MULX: multiply by x[keys[i] - seg * div.d]
+    int64_t* out_keys;      // compact output
+    double* out_sums;       // compact (or dense: y[seg])
+    int64_t* out_count;
+    uint64_t* state;        // [ntiles]
+    double* agg_val;        // [ntiles]
+    double* pre_val;        // [ntiles]
+    uint32_t epoch;
+};
+
+// padded position: one spare slot per 8 elements keeps the blocked reads conflict-free
+__device__ __forceinline__ int pad8(int e) { return e + (e >> 3); }
+
+template <typename T, bool MULX, bool DENSE>
+__global__ void __launch_bounds__(kRNT) reduce_by_key_kernel(const ReduceParams p) {
+    __shared__ int64_t s_key[kRTile + kRTile / 8];
+    __shared__ T s_val[kRTile + kRTile / 8];
+    __shared__ int64_t s_first_seg[kRNT + 1];     // first segment key of each thread (+ next tile's)
+    __shared__ int64_t s_last_seg[kRNT];
+    __shared__ int s_wheads[kRNT / 32];
+    __shared__ double s_wval[kRNT / 32];
+    __shared__ int s_wflag[kRNT / 32];
+    __shared__ int64_t s_tile_heads;
+    __shared__ double s_tile_carry;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tile = blockIdx.x;
+    const int64_t tile_start = tile * kRTile;
+    const int tile_items = (int)((p.n - tile_start) < kRTile ? (p.n - tile_start) : kRTile);
+    const T* vals = reinterpret_cast<const T*>(p.vals);
+
+    // coalesced striped loads -> padded smem
+#pragma unroll
+    for (int k = 0; k < kRVT; ++k) {
+        const int e = k * kRNT + tid;
+        if (e < tile_items) {
+            s_key[pad8(e)] = __ldcs(p.keys + tile_start + e);
+            s_val[pad8(e)] = __ldcs(vals + tile_start + e);
+        }
+    }
+    // segment key just before / after the tile (heads and ends at the tile borders)
+    int64_t prev_seg = -1, next_seg = -1;
+    if (tid == 0 && tile_start > 0) prev_seg = (int64_t)fastdiv((uint64_t)p.keys[tile_start - 1], p.div);
+    if (tid == kRNT - 1 && tile_start + tile_items < p.n)
+        next_seg = (int64_t)fastdiv((uint64_t)p.keys[tile_start + tile_items], p.div);
+    __syncthreads();
+
+    // blocked: thread t owns items [t*kRVT, t*kRVT + kRVT)
+    const int first = tid * kRVT;
+    int cnt = tile_items - first;
+    cnt = cnt < 0 ? 0 : (cnt > kRVT ? kRVT : cnt);
+    int64_t seg[kRVT];
+    double v[kRVT];
+#pragma unroll
+    for (int k = 0; k < kRVT; ++k) {
+        seg[k] = -2;
+        v[k] = 0.0;
+        if (k < cnt) {
+            const int64_t key = s_key[pad8(first + k)];
+            seg[k] = (int64_t)fastdiv((uint64_t)key, p.div);
+            double val = (double)s_val[pad8(first + k)];
+            if constexpr (MULX) {
+                const int64_t col = key - seg[k] * (int64_t)p.div.d;
+                val *= (double)__ldg(reinterpret_cast<const T*>(p.x) + col);
+            }
+            v[k] = val;
+        }
+    }
+    s_first_seg[tid] = cnt > 0 ? seg[0] : -3;
+    s_last_seg[tid] = cnt > 0 ? seg[cnt - 1] : -3;
+    if (tid == kRNT - 1) s_first_seg[kRNT] = next_seg;
+    __syncthreads();
+    // key preceding my first item: the last key of the nearest earlier thread that owns items
+    // (all earlier threads are full unless I own nothing), or the previous tile's last key
+    const int64_t before = tid == 0 ? prev_seg : s_last_seg[tid - 1];
+    // key following my last item (-1: nothing follows, the array ends)
+    const int64_t after = (first + cnt == tile_items) ? s_first_seg[kRNT] : s_first_seg[tid + 1];
+
+    // thread-sequential segmented scan
+    unsigned head_bits = 0;
+    int nheads = 0;
+    double run = 0.0;
+    double incl[kRVT];
+#pragma unroll
+    for (int k = 0; k < kRVT; ++k) {
+        if (k < cnt) {
+            const bool head = seg[k] != (k == 0 ? before : seg[k - 1]);
+            if (head) {
+                head_bits |= 1u << k;
+                ++nheads;
+                run = v[k];
+            } else {
+                run += v[k];
+            }
+            incl[k] = run;
+        }
+    }
+    // block exclusive scan of Carry(nheads, run, nheads > 0)
+    Carry mine{nheads, run, nheads > 0};
+    Carry inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Carry up;
+        up.heads = __shfl_up_sync(0xffffffffu, inc.heads, o);
+        up.val = __shfl_up_sync(0xffffffffu, inc.val, o);
+        up.flag = __shfl_up_sync(0xffffffffu, (int)inc.flag, o) != 0;
+        if (lane >= o) inc = combine(up, inc);
+    }
+    if (lane == 31) {
+        s_wheads[warp] = (int)inc.heads;
+        s_wval[warp] = inc.val;
+        s_wflag[warp] = inc.flag;
+    }
+    __syncthreads();
+    // exclusive prefix over earlier warps (8 warps: serial is fine), and the tile aggregate
+    Carry wpre{0, 0.0, false};
+    Carry tile_agg{0, 0.0, false};
+#pragma unroll
+    for (int w = 0; w < kRNT / 32; ++w) {
+        Carry c{s_wheads[w], s_wval[w], s_wflag[w] != 0};
+        if (w < warp) wpre = combine(wpre, c);
+        tile_agg = combine(tile_agg, c);
+    }
+    Carry lane_excl;   // exclusive within the warp
+    lane_excl.heads = __shfl_up_sync(0xffffffffu, inc.heads, 1);
+    lane_excl.val = __shfl_up_sync(0xffffffffu, inc.val, 1);
+    lane_excl.flag = __shfl_up_sync(0xffffffffu, (int)inc.flag, 1) != 0;
+    if (lane == 0) lane_excl = Carry{0, 0.0, false};
+    Carry excl = combine(wpre, lane_excl);      // everything in this tile before my first item
+
+    // ---- decoupled look-back (warp 0) ----------------------------------------------------------
+    if (warp == 0) {
+        int64_t heads_before = 0;
+        double carry = 0.0;
+        if (tile > 0) {
+            if (lane == 0) {
+                p.agg_val[tile] = tile_agg.val;
+                st_release(p.state + tile, pack_state(kStAgg, p.epoch,
+                                                      (uint64_t)tile_agg.heads | (tile_agg.flag ? kHeadFlag : 0)));
+            }
+            bool val_open = true;       // still extending the open-segment sum backwards
+            int64_t base = tile - 1;
+            while (base >= 0) {
+                const int64_t t = base - lane;
+                uint64_t w = pack_state(kStPrefix, p.epoch, 0);
+                double pv = 0.0;
+                if (t >= 0) {
+                    for (;;) {
+                        w = ld_acquire(p.state + t);
+                        if ((w >> 62) != 0 && (uint32_t)((w >> 48) & ((1u << kEpochBits) - 1)) == p.epoch) break;
+                        __nanosleep(20);
+                    }
+                    pv = ld_cg_f64(((w >> 62) == kStPrefix ? p.pre_val : p.agg_val) + t);
+                }
+                const unsigned has_prefix = __ballot_sync(0xffffffffu, (w >> 62) == kStPrefix);
+                const int stop = has_prefix ? (__ffs(has_prefix) - 1) : 31;
+                const unsigned flagged = __ballot_sync(0xffffffffu, (w & kHeadFlag) != 0 && lane <= stop);
+                const int vstop = flagged ? (__ffs(flagged) - 1) : stop;   // nearest tile holding a head
+                int64_t h = lane <= stop ? (int64_t)(w & kHeadCountMask) : 0;
+                double vv = (val_open && lane <= vstop) ? pv : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    h += __shfl_xor_sync(0xffffffffu, h, o);
+                    vv += __shfl_xor_sync(0xffffffffu, vv, o);
+                }
+                heads_before += h;
+                carry += vv;
+                if (flagged) val_open = false;
+                if (has_prefix) break;
+                base -= 32;
+            }
+        }
+        if (lane == 0) {
+            const Carry incl_prefix = combine(Carry{heads_before, carry, heads_before > 0}, tile_agg);
+            p.pre_val[tile] = incl_prefix.val;
+            st_release(p.state + tile, pack_state(kStPrefix, p.epoch,
+                                                  (uint64_t)incl_prefix.heads | (incl_prefix.flag ? kHeadFlag : 0)));
+            s_tile_heads = heads_before;
+            s_tile_carry = carry;
+            if (!DENSE && tile_start + tile_items == p.n) *p.out_count = incl_prefix.heads;
+        }
+    }
+    __syncthreads();
+    const int64_t heads_before_tile = s_tile_heads;
+    const double tile_carry = s_tile_carry;
+    // carry reaching my first item = (tile carry) (+) (in-tile exclusive)
+    const double carry_in = excl.flag ? excl.val : tile_carry + excl.val;
+    int64_t pos = heads_before_tile + excl.heads - 1;     // output slot of the segment open at my first item
+    bool seen_head = false;
+#pragma unroll
+    for (int k = 0; k < kRVT; ++k) {
+        if (k < cnt) {
+            if (head_bits & (1u << k)) {
+                ++pos;
+                seen_head = true;
+                if constexpr (!DENSE) p.out_keys[pos] = seg[k];
+            }
+            const int64_t nxt = (k + 1 < cnt) ? seg[k + 1] : after;
+            if (nxt != seg[k]) {   // segment ends here
+                const double total = seen_head ? incl[k] : carry_in + incl[k];
+                if constexpr (DENSE) p.out_sums[seg[k]] = total;
+                else p.out_sums[pos] = total;
+            }
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ T mm_op(T a, T b, int is_max) {
+    if constexpr (T(0.5) != T(0)) {
+        if (a != a) return a;
+        if (b != b) return b;
+    }
+    return is_max ? (a > b ? a : b) : (a < b ? a : b);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) min_max_kernel(const T* __restrict__ in, int64_t n, T* __restrict__ partial,
+                                                      int is_max) {
+    const int64_t start = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    T acc = in[start < n ? start : 0];
+    for (int64_t i = start; i < n; i += (int64_t)gridDim.x * blockDim.x) acc = mm_op<T>(acc, in[i], is_max);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = mm_op<T>(acc, __shfl_xor_sync(0xffffffffu, acc, o), is_max);
+    __shared__ T ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T t = ws[0];
+        for (int w = 1; w < 8; ++w) t = mm_op<T>(t, ws[w], is_max);
+        partial[blockIdx.x] = t;
+    }
+}
+
+// compaction of (idx, val) pairs by a byte mask, order preserving
+template <typename T>
+__global__ void __launch_bounds__(256) select_flagged_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
+                                                             const uint8_t* __restrict__ keep, int64_t n,
+                                                             int64_t* __restrict__ out_idx, T* __restrict__ out_val,
+                                                             int64_t* __restrict__ out_count, uint64_t* state,
+                                                             uint32_t epoch) {
+    constexpr int VT = 8;
+    __shared__ int warp_sums[8];
+    __shared__ int64_t tile_base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tile = blockIdx.x;
+    const int64_t first = tile * (256 * VT) + (int64_t)tid * VT;
+    unsigned bits = 0;
+#pragma unroll
+    for (int k = 0; k < VT; ++k)
+        if (first + k < n && keep[first + k]) bits |= 1u << k;
+    const int cnt = __popc(bits);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < 8 ? warp_sums[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        if (lane < 8) warp_sums[lane] = wi - w;
+        const int tile_total = __shfl_sync(0xffffffffu, wi, 7);
+        uint64_t base = 0;
+        if (tile == 0) {
+            if (lane == 0) st_state(state, pack_state(kStPrefix, epoch, (uint64_t)tile_total));
+        } else {
+            if (lane == 0) st_state(state + tile, pack_state(kStAgg, epoch, (uint64_t)tile_total));
+            base = lookback_exclusive(state, tile, epoch);
+            if (lane == 0) st_state(state + tile, pack_state(kStPrefix, epoch, base + (uint64_t)tile_total));
+        }
+        if (lane == 0) {
+            tile_base_s = (int64_t)base;
+            if (tile == gridDim.x - 1) *out_count = (int64_t)base + tile_total;
+        }
+    }
+    __syncthreads();
+    int64_t off = tile_base_s + warp_sums[warp] + incl - cnt;
+#pragma unroll
+    for (int k = 0; k < VT; ++k) {
+        if (bits & (1u << k)) {
+            out_idx[off] = idx[first + k];
+            out_val[off] = val[first + k];
+            ++off;
+        }
+    }
+}
+
+template <typename T, bool MULX, bool DENSE>
+int launch_reduce(ReduceParams& p, spb_workspace* ws, cudaStream_t stream) {
+    const int64_t ntiles = ceil_div(p.n, kRTile);
+    if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
+    int rc = workspace_reserve(ws, (size_t)ntiles * 8, stream);
+    if (rc) return rc;
+    rc = workspace_next_epoch(ws, stream, &p.epoch);
+    if (rc) return rc;
+    p.state = ws_state(ws);
+    rc = workspace_reserve_payload(ws, (size_t)ntiles * 8 * 2, stream);
+    if (rc) return rc;
+    p.agg_val = reinterpret_cast<double*>(ws->payload);
+    p.pre_val = p.agg_val + ntiles;
+    reduce_by_key_kernel<T, MULX, DENSE><<<(unsigned)ntiles, kRNT, 0, stream>>>(p);
+    SPB_LAUNCHED(1);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace spb
+
+using namespace spb;
+
+extern "C" {
+
+int spb_reduce_by_key(int dtype, const int64_t* keys, const void* vals, int64_t n, int64_t key_divisor,
+                      int64_t* out_keys, double* out_sums, int64_t* out_count, spb_workspace* ws,
+                      spb_stream_t stream) {
+    if (n < 0 || key_divisor < 1 || !out_count) return SPB_ERR_BAD_ARG;
+    if (n == 0) return (int)cudaMemsetAsync(out_count, 0, 8, stream);
+    if (!keys || !vals || !out_keys || !out_sums) return SPB_ERR_BAD_ARG;
+    ReduceParams p{};
+    p.keys = keys; p.vals = vals; p.n = n; p.div = make_fastdiv((uint64_t)key_divisor);
+    p.out_keys = out_keys; p.out_sums = out_sums; p.out_count = out_count;
+#define SPB_RBK(T) return launch_reduce<T, false, false>(p, ws, stream)
+    switch (dtype) {
+        case SPB_F32: SPB_RBK(float);
+        case SPB_F64: SPB_RBK(double);
+        case SPB_I32: SPB_RBK(int32_t);
+        case SPB_I64: SPB_RBK(int64_t);
+        case SPB_U8: SPB_RBK(uint8_t);
+        case SPB_BOOL: SPB_RBK(uint8_t);
+        case SPB_I8: SPB_RBK(int8_t);
+        case SPB_I16: SPB_RBK(int16_t);
+        default: return SPB_ERR_UNSUPPORTED;
+    }
+#undef SPB_RBK
+}
+
+int spb_spmv(int dtype, const int64_t* idx, const void* vals, int64_t n, int64_t ncols, int64_t nrows,
+             const void* x, double* y, spb_workspace* ws, spb_stream_t stream) {
+    if (n < 0 || ncols < 1 || nrows < 0) return SPB_ERR_BAD_ARG;
+    if (nrows == 0) return SPB_OK;
+    if (!y) return SPB_ERR_BAD_ARG;
+    SPB_CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)nrows * sizeof(double), stream));
+    if (n == 0) return SPB_OK;
+    if (!idx || !vals || !x) return SPB_ERR_BAD_ARG;
+    ReduceParams p{};
+    p.keys = idx; p.vals = vals; p.n = n; p.div = make_fastdiv((uint64_t)ncols);
+    p.x = x; p.out_sums = y;
+    switch (dtype) {
+        case SPB_F32: return launch_reduce<float, true, true>(p, ws, stream);
+        case SPB_F64: return launch_reduce<double, true, true>(p, ws, stream);
+        default: return SPB_ERR_UNSUPPORTED;
+    }
+}
+
+int spb_min_max(int dtype, const void* vals, int64_t n, int is_max, void* out, spb_workspace* ws,
+                spb_stream_t stream) {
+    if (n <= 0 || !vals || !out) return SPB_ERR_BAD_ARG;
+    int64_t b = ceil_div(n, 256 * 8);
+    const int nblocks = (int)(b > 1024 ? 1024 : b);
+    int rc = workspace_reserve(ws, 0, stream);
+    if (rc) return rc;
+    char* part = ws_misc(ws);
+#define SPB_MM(T)                                                                                  \
+    min_max_kernel<T><<<nblocks, 256, 0, stream>>>((const T*)vals, n, (T*)part, is_max);           \
+    SPB_LAUNCHED(1); \
+    min_max_kernel<T><<<1, 256, 0, stream>>>((const T*)part, nblocks, (T*)out, is_max);            \
+    SPB_LAUNCHED(1); \
+    return (int)cudaGetLastError()
+    switch (dtype) {
+        case SPB_F32: SPB_MM(float);
+        case SPB_F64: SPB_MM(double);
+        case SPB_I32: SPB_MM(int32_t);
+        case SPB_I64: SPB_MM(int64_t);
+        case SPB_U8: SPB_MM(uint8_t);
+        case SPB_BOOL: SPB_MM(uint8_t);
+        case SPB_I8: SPB_MM(int8_t);
+        case SPB_I16: SPB_MM(int16_t);
+        default: return SPB_ERR_UNSUPPORTED;
+    }
+#undef SPB_MM
+}
+
+int spb_select_flagged(int dtype, const int64_t* idx, const void* val, const uint8_t* keep, int64_t n,
+                       int64_t* out_idx, void* out_val, int64_t* out_count, spb_workspace* ws,
+                       spb_stream_t stream) {
+    if (n < 0 || !out_count) return SPB_ERR_BAD_ARG;
+    if (n == 0) return (int)cudaMemsetAsync(out_count, 0, 8, stream);
+    if (!idx || !val || !keep || !out_idx || !out_val) return SPB_ERR_BAD_ARG;
+    const int64_t ntiles = ceil_div(n, 256 * 8);
+    if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
+    int rc = workspace_reserve(ws, (size_t)ntiles * 8, stream);
+    if (rc) return rc;
+    uint32_t epoch;
+    rc = workspace_next_epoch(ws, stream, &epoch);
+    if (rc) return rc;
+#define SPB_SF(T)                                                                                             \
+    select_flagged_kernel<T><<<(unsigned)ntiles, 256, 0, stream>>>(idx, (const T*)val, keep, n, out_idx,     \
+                                                                   (T*)out_val, out_count, ws_state(ws), epoch); \
+    SPB_LAUNCHED(1); \
+    return (int)cudaGetLastError()
+    switch (dtype) {
+        case SPB_F32: SPB_SF(float);
+        case SPB_F64: SPB_SF(double);
+        case SPB_I32: SPB_SF(int32_t);
+        case SPB_I64: SPB_SF(int64_t);
+        case SPB_U8: SPB_SF(uint8_t);
+        case SPB_BOOL: SPB_SF(uint8_t);
+        case SPB_I8: SPB_SF(int8_t);
+        case SPB_I16: SPB_SF(int16_t);
+        default: return SPB_ERR_UNSUPPORTED;
+    }
+#undef SPB_SF
+}
+
+}  // extern "C"

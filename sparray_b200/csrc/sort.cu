@@ -1,0 +1,369 @@
+// sparray_b200/csrc/sort.cu -- index re-keying (unravel / permute or drop axes /
+// re-ravel) fused into a one-sweep LSD radix sort of (int64 key, value) pairs.
+//
+// Replaces the np.unravel_index / np.ravel_multi_index temporaries and the
+// argsort-based np.unique of FlatSparray.transpose (flat.py:109-112 + ctor :34),
+// of sum(axis != last) (flat.py:617-620) and of the non-canonical ctor.
+//
+//   histogram kernel : one read of the keys, all digit histograms at once
+//   one kernel per 8-bit digit: tile-local ranking by warp ballots (stable),
+//     per-digit decoupled look-back across tiles, exchange through shared memory,
+//     run-coalesced scatter.  The re-key arithmetic (shifts or mul-hi magic
+//     division, no 64-bit div instruction) is applied to the keys as they are
+//     loaded by the histogram and by the first pass, so the re-keyed index array
+//     is never materialised on its own.
+//   Only the digits that matter are sorted: the host passes a divisor that strips
+//   the trailing axes which already arrive in order (LSD sort is stable).
+#include "common.cuh"
+
+namespace spb {
+
+constexpr int kMaxRekeyDims = 8;
+constexpr int kSNT = 256;                 // threads (= radix, one digit per thread in the scan phases)
+constexpr int kSIPT = 16;                 // items per thread
+constexpr int kSTile = kSNT * kSIPT;      // 4096
+constexpr int kSWarps = kSNT / 32;
+constexpr int kMaxPasses = 8;
+
+struct Rekey {
+    int ndim;                             // 0: identity
+    FastDiv in_div[kMaxRekeyDims];        // C-order stride of (merged) axis ax in the old shape
+    int64_t out_mul[kMaxRekeyDims];       // its stride in the new shape; 0 = axis dropped
+};
+
+__device__ __forceinline__ int64_t apply_rekey(int64_t idx, const Rekey& r) {
+    if (r.ndim == 0) return idx;
+    uint64_t rem = (uint64_t)idx;
+    int64_t acc = 0;
+#pragma unroll
+    for (int ax = 0; ax < kMaxRekeyDims - 1; ++ax) {
+        if (ax < r.ndim - 1) {
+            const uint64_t q = fastdiv(rem, r.in_div[ax]);
+            rem -= q * r.in_div[ax].d;
+            acc += (int64_t)q * r.out_mul[ax];
+        }
+    }
+    return acc + (int64_t)rem * r.out_mul[r.ndim - 1];
+}
+
+struct SortParams {
+    const int64_t* keys_in;
+    const void* vals_in;
+    int64_t* keys_out;
+    void* vals_out;
+    int64_t n;
+    Rekey rk;
+    int do_rekey;
+    FastDiv sort_div;       // sort key = key / sort_div.d
+    int shift;              // this pass sorts bits [shift, shift + 8) of the sort key
+    int npasses;
+    uint64_t* hist;         // [kMaxPasses][256] counts, then exclusive offsets
+    uint64_t* state;        // [ntiles][256]
+    uint32_t epoch;
+};
+
+__device__ __forceinline__ uint64_t sort_key(int64_t key, const SortParams& p) {
+    return fastdiv((uint64_t)key, p.sort_div);
+}
+
+// ---- all digit histograms in one read --------------------------------------------------------
+__global__ void __launch_bounds__(kSNT) radix_hist_kernel(const SortParams p) {
+    __shared__ unsigned h[kMaxPasses * 256];
+    for (int i = threadIdx.x; i < p.npasses * 256; i += kSNT) h[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t nthreads = (int64_t)gridDim.x * kSNT;
+    // whole warps stay converged so the vote below is legal: iterate on a warp-aligned bound
+    const int64_t n_round = (p.n + 31) & ~(int64_t)31;
+    for (int64_t i = blockIdx.x * (int64_t)kSNT + threadIdx.x; i < n_round; i += nthreads) {
+        const bool valid = i < p.n;
+        uint64_t sk = 0;
+        if (valid) {
+            int64_t key = __ldcs(p.keys_in + i);
+            if (p.do_rekey) key = apply_rekey(key, p.rk);
+            sk = sort_key(key, p);
+        }
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        for (int ps = 0; ps < p.npasses; ++ps) {
+            const unsigned d = (unsigned)(sk >> (8 * ps)) & 255u;
+            const unsigned d0 = __shfl_sync(0xffffffffu, d, __ffs(vmask) - 1);
+            const bool uniform = __all_sync(0xffffffffu, !valid || d == d0);
+            if (uniform) {   // runs of equal digits (sorted input): one add per warp
+                if (lane == __ffs(vmask) - 1) atomicAdd(&h[ps * 256 + d], (unsigned)__popc(vmask));
+            } else if (valid) {
+                atomicAdd(&h[ps * 256 + d], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.npasses * 256; i += kSNT)
+        if (h[i]) atomicAdd(reinterpret_cast<unsigned long long*>(p.hist) + i, (unsigned long long)h[i]);
+}
+
+// counts -> exclusive offsets, one block per pass
+__global__ void __launch_bounds__(256) radix_scan_kernel(uint64_t* hist) {
+    __shared__ uint64_t s[256];
+    uint64_t* h = hist + blockIdx.x * 256;
+    const int t = threadIdx.x;
+    const uint64_t mine = h[t];
+    s[t] = mine;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        uint64_t add = t >= o ? s[t - o] : 0;
+        __syncthreads();
+        s[t] += add;
+        __syncthreads();
+    }
+    h[t] = s[t] - mine;
+}
+
+// ---- one digit pass -----------------------------------------------------------------------------
+template <typename V, bool HAS_VAL>
+__global__ void __launch_bounds__(kSNT) radix_pass_kernel(const SortParams p) {
+    __shared__ int64_t s_keys[kSTile];                 // keys, then values, in digit-sorted tile order
+    __shared__ uint8_t s_dig[kSTile];
+    __shared__ unsigned s_whist[kSWarps][256];
+    __shared__ int s_dstart[256];
+    __shared__ int64_t s_goff[256];
+    __shared__ int s_scan[kSWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int64_t tile = blockIdx.x;
+    const int64_t base = tile * kSTile;
+    const int items = (int)((p.n - base) < kSTile ? (p.n - base) : kSTile);
+    const int wbase = warp * 32 * kSIPT;
+
+    for (int i = tid; i < kSWarps * 256; i += kSNT) (&s_whist[0][0])[i] = 0;
+
+    int64_t keys[kSIPT];
+    uint8_t dig[kSIPT];
+    uint16_t rank[kSIPT];
+#pragma unroll
+    for (int k = 0; k < kSIPT; ++k) {
+        const int e = wbase + k * 32 + lane;
+        keys[k] = 0;
+        if (e < items) {
+            int64_t key = __ldcs(p.keys_in + base + e);
+            if (p.do_rekey) key = apply_rekey(key, p.rk);
+            keys[k] = key;
+        }
+    }
+    __syncthreads();
+
+    // tile-local stable ranking: per warp, item rows in order, lanes in order inside a row
+#pragma unroll
+    for (int k = 0; k < kSIPT; ++k) {
+        const int e = wbase + k * 32 + lane;
+        const bool valid = e < items;
+        const unsigned d = (unsigned)(sort_key(keys[k], p) >> p.shift) & 255u;
+        dig[k] = (uint8_t)d;
+        unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+            peers &= ((d >> b) & 1u) ? bal : ~bal;
+        }
+        if (!valid) peers = 0;
+        const int leader = peers ? (__ffs(peers) - 1) : lane;
+        unsigned old = 0;
+        if (valid && lane == leader) {
+            old = s_whist[warp][d];
+            s_whist[warp][d] = old + (unsigned)__popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[k] = (uint16_t)(old + (unsigned)__popc(peers & lt_mask));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // per digit (thread d): exclusive offsets across warps, tile count, look-back
+    {
+        const int d = tid;
+        unsigned sum = 0;
+#pragma unroll
+        for (int w = 0; w < kSWarps; ++w) {
+            const unsigned t = s_whist[w][d];
+            s_whist[w][d] = sum;
+            sum += t;
+        }
+        uint64_t* st = p.state + tile * 256 + d;
+        if (tile == 0) st_state(st, pack_state(kStPrefix, p.epoch, sum));
+        else st_state(st, pack_state(kStAgg, p.epoch, sum));
+
+        // block exclusive scan of `sum` over the 256 digits
+        int incl = (int)sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        int wofs = 0;
+#pragma unroll
+        for (int w = 0; w < kSWarps; ++w)
+            if (w < warp) wofs += s_scan[w];
+        const int dstart = wofs + incl - (int)sum;
+
+        uint64_t excl = 0;
+        if (tile > 0) {
+            int64_t t = tile - 1;
+            for (;;) {
+                uint64_t w;
+                for (;;) {
+                    w = ld_state(p.state + t * 256 + d);
+                    if ((w >> 62) != 0 && (uint32_t)((w >> 48) & ((1u << kEpochBits) - 1)) == p.epoch) break;
+                    __nanosleep(20);
+                }
+                excl += w & kCountMask;
+                if ((w >> 62) == kStPrefix || t == 0) break;
+                --t;
+            }
+            st_state(st, pack_state(kStPrefix, p.epoch, excl + sum));
+        }
+        s_dstart[d] = dstart;
+        s_goff[d] = (int64_t)(p.hist[(p.shift >> 3) * 256 + d] + excl) - dstart;
+    }
+    __syncthreads();
+
+    // exchange keys through shared memory into digit order
+#pragma unroll
+    for (int k = 0; k < kSIPT; ++k) {
+        const int e = wbase + k * 32 + lane;
+        if (e < items) {
+            const int r = s_dstart[dig[k]] + (int)s_whist[warp][dig[k]] + (int)rank[k];
+            rank[k] = (uint16_t)r;
+            s_keys[r] = keys[k];
+            s_dig[r] = dig[k];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kSIPT; ++j) {
+        const int q = j * kSNT + tid;
+        if (q < items) p.keys_out[s_goff[s_dig[q]] + q] = s_keys[q];
+    }
+    if constexpr (HAS_VAL) {
+        const V* vin = reinterpret_cast<const V*>(p.vals_in);
+        V* vout = reinterpret_cast<V*>(p.vals_out);
+        V vals[kSIPT];
+#pragma unroll
+        for (int k = 0; k < kSIPT; ++k) {
+            const int e = wbase + k * 32 + lane;
+            if (e < items) vals[k] = __ldcs(vin + base + e);
+        }
+        __syncthreads();                               // all key reads of s_keys are done
+        V* s_vals = reinterpret_cast<V*>(s_keys);
+#pragma unroll
+        for (int k = 0; k < kSIPT; ++k) {
+            const int e = wbase + k * 32 + lane;
+            if (e < items) s_vals[rank[k]] = vals[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kSIPT; ++j) {
+            const int q = j * kSNT + tid;
+            if (q < items) vout[s_goff[s_dig[q]] + q] = s_vals[q];
+        }
+    }
+}
+
+// no digits to sort: just re-key (and copy the values)
+template <typename V>
+__global__ void __launch_bounds__(256) rekey_copy_kernel(const SortParams p) {
+    const V* vin = reinterpret_cast<const V*>(p.vals_in);
+    V* vout = reinterpret_cast<V*>(p.vals_out);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t key = p.keys_in[i];
+        if (p.do_rekey) key = apply_rekey(key, p.rk);
+        p.keys_out[i] = key;
+        if (vin) vout[i] = vin[i];
+    }
+}
+
+template <typename V>
+int run_sort(SortParams p, int sort_bits, int64_t* tmp_keys, void* tmp_vals, spb_workspace* ws, cudaStream_t stream) {
+    const int npasses = (sort_bits + 7) / 8;
+    int64_t* const final_keys = p.keys_out;
+    void* const final_vals = p.vals_out;
+    if (npasses == 0) {
+        int64_t blocks = ceil_div(p.n, 256 * 4);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        rekey_copy_kernel<V><<<(unsigned)blocks, 256, 0, stream>>>(p);
+        SPB_LAUNCHED(1);
+        return (int)cudaGetLastError();
+    }
+    if (npasses > kMaxPasses) return SPB_ERR_BAD_ARG;
+    if (npasses > 1 && (!tmp_keys || (p.vals_in && !tmp_vals))) return SPB_ERR_BAD_ARG;
+    const int64_t ntiles = ceil_div(p.n, kSTile);
+    if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
+    int rc = workspace_reserve(ws, (size_t)ntiles * 256 * 8, stream);
+    if (rc) return rc;
+    p.npasses = npasses;
+    p.hist = reinterpret_cast<uint64_t*>(ws_misc(ws) + (512 << 10));     // upper half of the misc slab
+    p.state = ws_state(ws);
+    SPB_CUDA_TRY(cudaMemsetAsync(p.hist, 0, sizeof(uint64_t) * kMaxPasses * 256, stream));
+    int64_t hblocks = ceil_div(p.n, kSNT * 16);
+    if (hblocks > 148 * 8) hblocks = 148 * 8;
+    radix_hist_kernel<<<(unsigned)hblocks, kSNT, 0, stream>>>(p);
+    SPB_LAUNCHED(1);
+    radix_scan_kernel<<<npasses, 256, 0, stream>>>(p.hist);
+    SPB_LAUNCHED(1);
+    const bool has_val = p.vals_in != nullptr;
+    for (int ps = 0; ps < npasses; ++ps) {
+        const bool to_final = ((npasses - 1 - ps) % 2) == 0;
+        p.keys_out = to_final ? final_keys : tmp_keys;
+        p.vals_out = to_final ? final_vals : tmp_vals;
+        p.shift = 8 * ps;
+        rc = workspace_next_epoch(ws, stream, &p.epoch);
+        if (rc) return rc;
+        if (has_val) {
+            radix_pass_kernel<V, true><<<(unsigned)ntiles, kSNT, 0, stream>>>(p);
+        } else {
+            radix_pass_kernel<V, false><<<(unsigned)ntiles, kSNT, 0, stream>>>(p);
+        }
+        SPB_LAUNCHED(1);
+        SPB_CUDA_TRY(cudaGetLastError());
+        p.keys_in = p.keys_out;
+        p.vals_in = p.vals_out;
+        p.do_rekey = 0;
+    }
+    return SPB_OK;
+}
+
+}  // namespace spb
+
+using namespace spb;
+
+extern "C" {
+
+int spb_rekey_sort(int dtype, const int64_t* idx, const void* val, int64_t n, int ndim,
+                   const int64_t* in_strides, const int64_t* out_strides, int64_t sort_divisor, int sort_bits,
+                   int64_t* out_idx, void* out_val, int64_t* tmp_idx, void* tmp_val, spb_workspace* ws,
+                   spb_stream_t stream) {
+    if (n < 0 || ndim < 0 || ndim > kMaxRekeyDims || sort_divisor < 1 || sort_bits < 0 || sort_bits > 63)
+        return SPB_ERR_BAD_ARG;
+    if (n == 0) return SPB_OK;
+    if (!idx || !out_idx || (val && !out_val) || (ndim && (!in_strides || !out_strides))) return SPB_ERR_BAD_ARG;
+    SortParams p{};
+    p.keys_in = idx; p.vals_in = val; p.keys_out = out_idx; p.vals_out = out_val; p.n = n;
+    p.rk.ndim = ndim;
+    p.do_rekey = ndim > 0;
+    for (int ax = 0; ax < ndim; ++ax) {
+        if (in_strides[ax] < 1 || out_strides[ax] < 0) return SPB_ERR_BAD_ARG;
+        p.rk.in_div[ax] = make_fastdiv((uint64_t)in_strides[ax]);
+        p.rk.out_mul[ax] = out_strides[ax];
+    }
+    if (ndim && in_strides[ndim - 1] != 1) return SPB_ERR_BAD_ARG;
+    p.sort_div = make_fastdiv((uint64_t)sort_divisor);
+    switch (dtype) {
+        case SPB_F32: case SPB_I32: return run_sort<uint32_t>(p, sort_bits, tmp_idx, tmp_val, ws, stream);
+        case SPB_F64: case SPB_I64: return run_sort<uint64_t>(p, sort_bits, tmp_idx, tmp_val, ws, stream);
+        case SPB_U8: case SPB_BOOL: case SPB_I8: return run_sort<uint8_t>(p, sort_bits, tmp_idx, tmp_val, ws, stream);
+        case SPB_I16: return run_sort<uint16_t>(p, sort_bits, tmp_idx, tmp_val, ws, stream);
+        default: return SPB_ERR_UNSUPPORTED;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,495 @@
+"""FlatSparray on a B200: the host-side mirror of the reference's
+``sparray/flat.py``.  Same class name, attributes (``indices``, ``data``,
+``shape``), method names, argument meaning and error behaviour -- but
+``indices`` (sorted unique int64 C-order flat indices) and ``data`` are
+device-resident ``torch`` tensors and every piece of arithmetic is a
+hand-written sm_100a CUDA kernel reached through the C ABI
+(include/sparray_b200.h).  There is no CPU fallback: without the CUDA library
+and a GPU, construction raises.
+
+Deliberate divergences from the reference:
+  * ``transpose`` is correct when the permuted shape equals the shape
+    (flat.py:106-107 returns ``self`` there -- SURVEY.md F5);
+  * ``swapaxes`` exists (absent upstream, F2);
+  * ``dot`` with a dense vector is an O(nnz) SpMV (flat.py:568 densifies, F7);
+  * ``__getitem__`` returns sorted (canonical) results for unsorted fancy
+    queries and numpy semantics for repeated ones;
+  * branches that densify (sparse + nonzero scalar, sparse / sparse, ...) and
+    mixed dense-ndarray operands are out of the hot-path scope and raise
+    NotImplementedError.
+"""
+import numbers
+import warnings
+
+import numpy as np
+import torch
+
+from . import _dtypes as dt
+from . import _indexing as ix
+from . import _kernels as _k
+from .base import _BaseSparray
+
+try:  # only for the warning category and spmatrix interop; never for arithmetic
+    import scipy.sparse as ss
+    _EfficiencyWarning = ss.SparseEfficiencyWarning
+except Exception:  # pragma: no cover
+    ss = None
+    _EfficiencyWarning = UserWarning
+
+_FIXED_POINT_AT_ZERO = ("sin", "tan", "arcsin", "arctan", "sinh", "tanh", "arcsinh", "arctanh", "rint", "sign",
+                        "expm1", "log1p", "deg2rad", "rad2deg", "floor", "ceil", "trunc", "sqrt")   # compat.py:96-102
+
+
+def _device():
+    _k.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_device(x, dtype=None):
+    """numpy / list / torch (any device) -> contiguous 1-D tensor on the current CUDA device."""
+    dev = _device()
+    if isinstance(x, torch.Tensor):
+        t = x.to(dev)
+    else:
+        arr = np.asarray(x)
+        if arr.dtype == object or arr.dtype.kind in "US":
+            raise TypeError("unsupported data type %s" % arr.dtype)
+        if arr.dtype.kind == "f" and arr.size == 0 and dtype is None:
+            arr = arr.astype(np.float64)
+        dt.torch_dtype(arr.dtype)      # raises TypeError for dtypes with no device form
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+    if dtype is not None and t.dtype != dtype:
+        t = _k.cast(t.contiguous().reshape(-1), dtype) if t.numel() else t.to(dtype)
+    return t.contiguous().reshape(-1)
+
+
+def _is_scalar(x):
+    return np.isscalar(x) or (isinstance(x, (np.ndarray, torch.Tensor)) and x.ndim == 0)
+
+
+class FlatSparray(_BaseSparray):
+    """Simple sparse ndarray-like, similar to scipy.sparse matrices.
+    Defined by three member variables (flat.py:19-25):
+      self.data : device tensor of nonzero values (may include zeros)
+      self.indices : sorted int64 device tensor of nonzero flat indices
+      self.shape : tuple of integers, ala ndarray shape
+    """
+
+    def __init__(self, indices, data, shape=None, is_canonical=False):    # flat.py:27-42
+        indices = _to_device(indices, torch.int64)
+        data = _to_device(data)
+        assert len(indices) == len(data), "# inds (%d) != # data (%d)" % (len(indices), len(data))
+        if not is_canonical:
+            # sort and sum duplicates, but allow explicit zeros (flat.py:32-35)
+            indices, data = _k.canonicalize(indices, data)
+        if shape is None:
+            self.shape = (int(indices[-1].item()) + 1,)
+        else:
+            self.shape = tuple(int(s) for s in shape)
+            assert np.prod(self.shape, dtype=object) >= len(data)
+        self.indices = indices
+        self.data = data
+
+    # -- basic properties ---------------------------------------------------------------------
+    @property
+    def dtype(self):
+        return dt.np_dtype(self.data.dtype)
+
+    def getnnz(self):
+        """Get the count of explicitly-stored values"""
+        return int(self.indices.numel())
+
+    nnz = property(fget=getnnz, doc=getnnz.__doc__)
+
+    def _size(self):
+        return int(np.prod(self.shape, dtype=object))
+
+    # -- converters (flat.py:48-82) -------------------------------------------------------------
+    @staticmethod
+    def from_ndarray(arr):
+        """Converts an array-like (host or device) to a FlatSparray object."""
+        shape = tuple(arr.shape) if hasattr(arr, "shape") else np.shape(arr)
+        dense = _to_device(arr)
+        idx, val = _k.select_nonzero(dense)
+        return FlatSparray(idx, val, shape=shape, is_canonical=True)
+
+    @staticmethod
+    def from_spmatrix(mat):
+        """Converts a scipy.sparse matrix to a FlatSparray object"""
+        try:
+            mat.sum_duplicates()
+        except AttributeError:
+            pass
+        mat = mat.tocoo()
+        inds = mat.row.astype(np.int64) * mat.shape[1] + mat.col.astype(np.int64)
+        return FlatSparray(inds, mat.data, shape=mat.shape, is_canonical=False)
+
+    def toarray(self):
+        """Dense numpy array (device scatter, then one device-to-host copy)."""
+        return self.todense_device().cpu().numpy()
+
+    def todense_device(self):
+        return _k.scatter_dense(self.indices, self.data, self._size()).reshape(self.shape)
+
+    def tocoo(self):
+        assert len(self.shape) == 2
+        idx = self.indices.cpu().numpy()
+        row, col = np.divmod(idx, self.shape[1])
+        return ss.coo_matrix((self.data.cpu().numpy(), (row, col)), shape=self.shape)
+
+    def to_numpy(self):
+        """(indices, data) as host numpy arrays."""
+        return self.indices.cpu().numpy(), self.data.cpu().numpy()
+
+    def nonzero(self):
+        """Tuple of host index arrays of the non-zero stored elements (flat.py:91-95)."""
+        keep = _k.unary_map("ne_s", self.data, 0)
+        idx, _ = _k.select_pairs(self.indices, self.data, keep)
+        return np.unravel_index(idx.cpu().numpy(), self.shape)
+
+    # -- axis permutation (flat.py:97-112) -------------------------------------------------------
+    def transpose(self, *axes):
+        ndim = len(self.shape)
+        if ndim < 2:
+            return self
+        if not axes:
+            axes = tuple(range(ndim - 1, -1, -1))
+        elif len(axes) == 1 and ndim > 1:
+            axes = tuple(axes[0])
+        axes = tuple(int(a) + ndim if int(a) < 0 else int(a) for a in axes)
+        if sorted(axes) != list(range(ndim)):
+            raise ValueError("axes don't match array")
+        if axes == tuple(range(ndim)):
+            return self
+        new_shape = tuple(self.shape[a] for a in axes)
+        new_idx, new_val = _k.transpose(self.indices, self.data, self.shape, axes)
+        return FlatSparray(new_idx, new_val, new_shape, is_canonical=True)
+
+    def swapaxes(self, axis1, axis2):
+        """numpy.swapaxes; sugar over transpose (absent upstream)."""
+        ndim = len(self.shape)
+        axes = list(range(ndim))
+        a1, a2 = int(axis1) % ndim, int(axis2) % ndim
+        axes[a1], axes[a2] = axes[a2], axes[a1]
+        return self.transpose(*axes)
+
+    # -- diagonal (flat.py:114-137) ----------------------------------------------------------------
+    def diagonal(self, offset=0, axis1=0, axis2=1):
+        if axis1 == axis2:
+            raise ValueError("axis1 and axis2 cannot be the same")
+        if len(self.shape) < 2:
+            raise ValueError("diagonal requires at least two dimensions")
+        if len(self.shape) > 2:
+            raise NotImplementedError("diagonal() is NYI for ndim > 2")
+        if axis1 != 0 or axis2 != 1:
+            raise NotImplementedError("diagonal() is NYI for non-default axes")
+        if offset >= 0:
+            n = min(self.shape[0], self.shape[1] - offset)
+            ranges = [[0, n, 1], [offset, n + offset, 1]]
+        else:
+            n = min(self.shape[0] + offset, self.shape[1])
+            ranges = [[-offset, n - offset, 1], [0, n, 1]]
+        if n <= 0:
+            return FlatSparray([], np.zeros(0, self.dtype), shape=(0,), is_canonical=True)
+        flat_idx = _k.combine_ranges(ranges, self.shape, n, inner=True, device=self.indices.device)
+        return self._getitem_flatidx(flat_idx, (n,))
+
+    def __repr__(self):
+        return "<%s-FlatSparray of type %s\n\twith %d stored elements>" % (self.shape, self.dtype, self.getnnz())
+
+    def __str__(self):
+        idx, data = self.to_numpy()
+        multi = np.unravel_index(idx, self.shape) if len(idx) else [[] for _ in self.shape]
+        return "\n".join("  %s\t%s" % (x[1:], x[0]) for x in zip(data, *multi))
+
+    # -- reshape family: metadata only, buffers shared (flat.py:173-191) ---------------------------
+    def reshape(self, new_shape):
+        new_shape = list(new_shape) if not isinstance(new_shape, numbers.Integral) else [new_shape]
+        if -1 in new_shape:
+            assert sum(d == -1 for d in new_shape) == 1, "Only one -1 allowed"
+            k = new_shape.index(-1)
+            new_shape[k] = self._size() // -int(np.prod(new_shape, dtype=object))
+        else:
+            assert np.prod(new_shape, dtype=object) >= len(self.data)
+        return FlatSparray(self.indices, self.data, shape=new_shape, is_canonical=True)
+
+    def resize(self, new_shape):
+        assert np.prod(new_shape, dtype=object) >= len(self.data)
+        self.shape = tuple(int(s) for s in new_shape)
+
+    def ravel(self):
+        return FlatSparray(self.indices, self.data, shape=(self._size(),), is_canonical=True)
+
+    # -- indexing (flat.py:193-325, 366-393) --------------------------------------------------------
+    def __getitem__(self, indices):
+        items, kind = ix.prepare_indices(indices, self.shape)
+        if kind == ix.EMPTY_SLICE_INDEX_MASK:                         # all colons
+            return self
+        if kind == ix.INTEGER_INDEX_MASK:                             # scalar lookup
+            flat = int(np.ravel_multi_index(items, self.shape))
+            q = torch.tensor([flat], dtype=torch.int64, device=self.indices.device)
+            pos, found = _k.lower_bound(self.indices, q)
+            if not bool(found.item()):
+                return 0
+            return self.data[pos[0]].cpu().numpy()[()]
+        if not (kind & ix.ARRAY_INDEX_MASK):                          # ints + slices: a box
+            ranges, new_shape = ix.indices_to_ranges(items, self.shape)
+            if any(s == 0 for s in new_shape):
+                return FlatSparray([], np.zeros(0, self.dtype), tuple(new_shape), is_canonical=True)
+            if np.any(ranges[:, 2] < 0):
+                raise NotImplementedError("negative slice steps are not supported")
+            new_idx, new_val = _k.getitem_box(self.indices, self.data, self.shape, ranges, new_shape)
+            return FlatSparray(new_idx, new_val, tuple(new_shape), is_canonical=True)
+        # fancy: per-output-axis offset arrays, outer-summed on the device
+        offsets, new_shape = ix.fancy_plan(items, self.shape)
+        if any(s == 0 for s in new_shape):
+            return FlatSparray([], np.zeros(0, self.dtype), tuple(new_shape), is_canonical=True)
+        query = _k.outer_sum(offsets, new_shape, self.indices.device)
+        return self._getitem_flatidx(query, new_shape)
+
+    def _getitem_flatidx(self, flat_idx, new_shape, is_sorted=True):     # flat.py:383-393
+        """Result index = position in the query; one binary search per query cell
+        (O(q log nnz), no sort of the query, repeated / unsorted queries fine)."""
+        new_idx, new_val = _k.lookup_compact(self.indices, self.data, flat_idx)
+        return FlatSparray(new_idx, new_val, tuple(new_shape), is_canonical=True)
+
+    def __setitem__(self, indices, val):                                  # flat.py:327-364
+        raise NotImplementedError("assignment is outside the hot-path scope of sparray_b200 (SURVEY.md 8f)")
+
+    def setdiag(self, values, offset=0):                                  # flat.py:139-160
+        raise NotImplementedError("setdiag is outside the hot-path scope of sparray_b200 (SURVEY.md 8f)")
+
+    # -- sparse (op) sparse helpers (flat.py:409-434) ---------------------------------------------
+    def _promoted(self, other, op):
+        """Values of both operands in np.promote_types(a, b) (flat.py:415)."""
+        a_val, b_val = self.data, other.data
+        if a_val.dtype != b_val.dtype:
+            common = dt.promote(a_val.dtype, b_val.dtype)
+            if a_val.dtype != common:
+                a_val = _k.cast(a_val, common)
+            if b_val.dtype != common:
+                b_val = _k.cast(b_val, common)
+        if a_val.dtype == torch.bool and op == "sub":
+            raise TypeError("numpy boolean subtract, the `-` operator, is not supported")
+        return a_val, b_val
+
+    def _pairwise_sparray(self, other, op):
+        """op(sparse, sparse) -> sparse on the UNION of the index sets; one fused kernel."""
+        a_val, b_val = self._promoted(other, op)
+        idx, val = _k.setop_binop("union", op, self.indices, a_val, other.indices, b_val)
+        return FlatSparray(idx, val, self.shape, is_canonical=True)
+
+    def _pairwise_sparray_fixed_zero(self, other, op):
+        """op(sparse, sparse) -> sparse on the INTERSECTION (op(x, 0) == 0); one fused kernel."""
+        a_val, b_val = self._promoted(other, op)
+        idx, val = _k.setop_binop("intersect", op, self.indices, a_val, other.indices, b_val)
+        return FlatSparray(idx, val, self.shape, is_canonical=True)
+
+    def _check_operand(self, other, what):
+        if ss is not None and ss.issparse(other):
+            other = FlatSparray.from_spmatrix(other)
+        if not isinstance(other, FlatSparray):
+            raise NotImplementedError("FlatSparray %s dense operand densifies or leaves the sorted-index path; "
+                                      "out of sparray_b200's scope" % what)
+        if other.shape != self.shape:
+            raise NotImplementedError("broadcasting densifies in the reference (flat.py:470-472); "
+                                      "out of sparray_b200's scope")
+        return other
+
+    def _comparison(self, other, method_name, op, op_symbol):              # flat.py:474-488
+        if _is_scalar(other):
+            np_op = getattr(np, {"lt": "less", "le": "less_equal", "gt": "greater", "ge": "greater_equal",
+                                 "eq": "equal", "ne": "not_equal"}[op])
+            if not np_op(0, other):
+                return self._scalar_map(op + "_s", other, compare=True)
+            kind = "nonzero scalar" if other != 0 else "0"
+            warnings.warn("FlatSparray %s %s densifies" % (op_symbol, kind), _EfficiencyWarning)
+            raise NotImplementedError("densifying comparison is out of sparray_b200's scope")
+        other = self._check_operand(other, op_symbol)
+        return self._pairwise_sparray(other, op)
+
+    def __add__(self, other):                                              # flat.py:490-505
+        if _is_scalar(other):
+            if other == 0:
+                return self.copy()
+            warnings.warn("FlatSparray + nonzero scalar densifies", _EfficiencyWarning)
+            raise NotImplementedError("densifying add is out of sparray_b200's scope")
+        return self._pairwise_sparray(self._check_operand(other, "+"), "add")
+
+    def __sub__(self, other):                                              # base.py:45-46
+        # a - b == a + (-b) bit for bit (IEEE / two's complement); fused so -b is never materialised
+        if _is_scalar(other):
+            return self.__add__(-other)
+        return self._pairwise_sparray(self._check_operand(other, "-"), "sub")
+
+    def __mul__(self, other):                                              # flat.py:507-518
+        if _is_scalar(other):
+            return self._scalar_map("mul_s", other)
+        return self._pairwise_sparray_fixed_zero(self._check_operand(other, "*"), "mul")
+
+    def _divide(self, other, div_func="divide", rdivide=False):            # flat.py:520-536
+        if rdivide or not _is_scalar(other):
+            raise NotImplementedError("this division densifies in the reference (flat.py:522-527); out of scope")
+        if div_func == "true_divide" or (div_func == "divide"):
+            return self.__mul__(1. / other)                                # flat.py:528-529
+        return self._scalar_map("floordiv_s", other)
+
+    def dot(self, other):                                                  # flat.py:538-568
+        ax1 = len(self.shape) - 1
+        oshape = tuple(other.shape)
+        ax2 = max(0, len(oshape) - 2)
+        if self.shape[ax1] != oshape[ax2]:
+            raise ValueError("shapes %s and %s not aligned" % (self.shape, oshape))
+        if len(oshape) != 1:
+            raise NotImplementedError("dot with a matrix operand (SpMM / SpGEMM) is out of scope (SURVEY.md 8f-4)")
+        nrows = self._size() // self.shape[ax1] if self.shape[ax1] else 0
+        if isinstance(other, FlatSparray):                                 # sparse vector: sparse result
+            x = other.todense_device().reshape(-1)
+            vdt = dt.promote(self.data.dtype, x.dtype)
+            y = _k.spmv(self.indices, self.data, self.shape[ax1], nrows, x, vdt)
+            if len(self.shape) == 1:
+                return y.cpu().numpy()[0]
+            return FlatSparray.from_ndarray(y.reshape(self.shape[:-1]))
+        x = _to_device(other)
+        vdt = dt.promote(self.data.dtype, x.dtype)
+        y = _k.spmv(self.indices, self.data, self.shape[ax1], nrows, x, vdt)
+        if len(self.shape) == 1:
+            return y.cpu().numpy()[0]                                      # flat.py:564-566
+        return y.reshape(self.shape[:-1]).cpu().numpy()                    # dense rhs -> dense result
+
+    def __pow__(self, exponent):                                           # flat.py:570-578
+        if exponent == 0:
+            warnings.warn("FlatSparray ** 0 densifies", _EfficiencyWarning)
+            raise NotImplementedError("densifying power is out of sparray_b200's scope")
+        elif exponent < 0:
+            warnings.warn("FlatSparray ** negative exponent densifies", _EfficiencyWarning)
+            raise NotImplementedError("densifying power is out of sparray_b200's scope")
+        return self._scalar_map("pow_s", exponent)
+
+    def _with_data(self, data):                                            # flat.py:580-581
+        return FlatSparray(self.indices.clone(), data, self.shape, is_canonical=True)
+
+    def _scalar_map(self, op, scalar, compare=False):
+        """data (op) python/numpy scalar with numpy's result dtype."""
+        if isinstance(scalar, (torch.Tensor, np.ndarray)):
+            scalar = scalar.item()
+        if isinstance(scalar, complex) or np.iscomplexobj(scalar):
+            raise TypeError("complex values are not supported by the sparray_b200 CUDA kernels")
+        np_dt = self.dtype
+        if compare:
+            res = np.result_type(np_dt, scalar) if np_dt != np.bool_ else np.result_type(np.int64, scalar)
+        elif op == "mul_s" and np_dt == np.bool_ and isinstance(scalar, (bool, np.bool_)):
+            res = np.dtype(np.bool_)
+        else:
+            res = np.result_type(np_dt, scalar)
+            if res == np.bool_:
+                res = np.dtype(np.int64)
+        data = self.data
+        tdt = dt.torch_dtype(res)
+        if data.dtype != tdt:
+            data = _k.cast(data, tdt)
+        return self._with_data(_k.unary_map(op, data, scalar))
+
+    def _float_map(self, op):
+        data = self.data
+        if not data.dtype.is_floating_point:
+            data = _k.cast(data, torch.float64)
+        return self._with_data(_k.unary_map(op, data))
+
+    def minimum(self, other):                                              # flat.py:583-593
+        if _is_scalar(other) and other >= 0:
+            return self._scalar_map("min_s", other)
+        if _is_scalar(other):
+            raise NotImplementedError("minimum with a negative scalar densifies; out of scope")
+        return self._pairwise_sparray(self._check_operand(other, "minimum"), "minimum")
+
+    def maximum(self, other):                                              # flat.py:595-605
+        if _is_scalar(other) and other <= 0:
+            return self._scalar_map("max_s", other)
+        if _is_scalar(other):
+            raise NotImplementedError("maximum with a positive scalar densifies; out of scope")
+        return self._pairwise_sparray(self._check_operand(other, "maximum"), "maximum")
+
+    # -- reductions (flat.py:607-626) --------------------------------------------------------------
+    def sum(self, axis=None, dtype=None):
+        if dtype is None:
+            dtype = self.dtype
+        dtype = np.dtype(dtype)
+        if dtype.kind == "c":
+            raise TypeError("complex values are not supported by the sparray_b200 CUDA kernels")
+        if axis is not None:
+            axis = int(axis)
+            if axis < 0:
+                axis += len(self.shape)
+        new_shape = None if axis is None else self.shape[:axis] + self.shape[axis + 1:]
+        if not new_shape:
+            total = _k.sum_all(self.data)
+            if dtype == np.bool_:
+                return np.bool_(total != 0)
+            return dtype.type(total)
+        # float64 output whatever the input dtype, like np.bincount(weights=)
+        new_idx, new_val = _k.sum_axis(self.indices, self.data, self.shape, axis)
+        return FlatSparray(new_idx, new_val, shape=new_shape, is_canonical=True)
+
+    # -- unary data ops (flat.py:677-739) -----------------------------------------------------------
+    def __abs__(self):
+        return self._with_data(_k.unary_map("abs", self.data))
+
+    def __neg__(self):
+        if self.data.dtype == torch.bool:
+            raise TypeError("The numpy boolean negative, the `-` operator, is not supported")
+        return self._with_data(_k.unary_map("neg", self.data))
+
+    @property
+    def real(self):
+        return self.copy()
+
+    @property
+    def imag(self):
+        return self._with_data(torch.zeros_like(self.data))
+
+    def __imul__(self, other):
+        if _is_scalar(other):
+            out = self._scalar_map("mul_s", other)
+            if out.data.dtype != self.data.dtype:
+                raise TypeError("Cannot cast ufunc 'multiply' output from %s to %s" % (out.dtype, self.dtype))
+            self.data = out.data
+            return self
+        return NotImplemented
+
+    def __itruediv__(self, other):
+        if _is_scalar(other):
+            recip = 1.0 / other
+            out = self._scalar_map("mul_s", recip)
+            if out.data.dtype != self.data.dtype:
+                raise TypeError("Cannot cast ufunc 'multiply' output from %s to %s" % (out.dtype, self.dtype))
+            self.data = out.data
+            return self
+        return NotImplemented
+
+    def astype(self, t):
+        return self._with_data(_k.cast(self.data, dt.torch_dtype(np.dtype(t))))
+
+    def conj(self):
+        return self.copy()
+
+    def copy(self):
+        return self._with_data(self.data.clone())
+
+    def min(self):
+        return self.dtype.type(_k.min_max(self.data, "min"))
+
+    def max(self):
+        return self.dtype.type(_k.min_max(self.data, "max"))
+
+
+def _make_unary(name):
+    def method(self):
+        return self._float_map(name)
+    method.__doc__ = "Element-wise %s.\n\nSee numpy.%s for more information." % (name, name)
+    method.__name__ = name
+    return method
+
+
+for _name in _FIXED_POINT_AT_ZERO:                                        # flat.py:722-739
+    setattr(FlatSparray, _name, _make_unary(_name))

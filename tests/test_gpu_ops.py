@@ -1,0 +1,257 @@
+"""GPU parity: transpose / swapaxes / reshape, axis sums, dot (SpMV), __getitem__,
+value maps and the non-canonical ctor -- against the golden fixtures (produced by
+the reference) and against the CPU oracle on seeded random inputs.
+
+Tolerances (north_star): indices and moved values bit-exact; float64 reductions
+and dot 1e-12 relative, float32 1e-5 relative (relative to the largest output)."""
+import numpy as np
+import pytest
+
+import golden_runner as gr
+from gpu_util import assert_sparse_same, fo, rand_operand, to_np
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {np.dtype(np.float64): 1e-12, np.dtype(np.float32): 1e-5, np.dtype(np.int64): 1e-12,
+        np.dtype(np.int32): 1e-12}
+
+
+@pytest.fixture(scope="module")
+def sp():
+    import sparray_b200
+    return sparray_b200
+
+
+@pytest.mark.parametrize("case", [c for op in ("transpose", "reduce", "dot_vec", "dot_1d", "getitem", "unary", "ctor")
+                                  for c in gr.cases(op)], ids=lambda c: c["name"])
+def test_golden(sp, case):
+    gr.check_case(case, gr.run_case(case, sp.FlatSparray))
+
+
+SHAPES = [((300, 500), 40000), ((37, 41, 43), 30000), ((16, 8, 32, 12), 25000), ((64, 64, 64, 16), 300000),
+          ((5, 1, 7, 1, 9), 200), ((2 ** 20, 2 ** 18), 100000)]
+
+
+@pytest.mark.parametrize("shape,nnz", SHAPES)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64], ids=lambda d: np.dtype(d).name)
+def test_transpose_random(sp, shape, nnz, dtype):
+    rng = np.random.default_rng(len(shape) * 1000 + nnz)
+    idx, val = rand_operand(rng, shape, nnz, dtype)
+    A = sp.FlatSparray(idx, val, shape=shape, is_canonical=True)
+    perms = [tuple(range(len(shape) - 1, -1, -1))]
+    for _ in range(4):
+        perms.append(tuple(rng.permutation(len(shape)).tolist()))
+    for axes in perms:
+        got = A.transpose(*axes)
+        want = fo.transpose(idx, val, shape, axes)
+        assert_sparse_same(got, want)
+    assert_sparse_same(A.T, fo.transpose(idx, val, shape, None))
+    if len(shape) >= 3:
+        got = A.swapaxes(0, 2)
+        axes = list(range(len(shape)))
+        axes[0], axes[2] = 2, 0
+        assert_sparse_same(got, fo.transpose(idx, val, shape, axes))
+
+
+def test_transpose_shape_preserving_permutation(sp):
+    """the reference returns self here; numpy semantics are the arbiter."""
+    rng = np.random.default_rng(2)
+    for shape, axes in [((40, 40), (1, 0)), ((8, 8, 8), (2, 1, 0)), ((16, 16, 16, 4), (2, 1, 0, 3))]:
+        idx, val = rand_operand(rng, shape, 500, np.float64)
+        A = sp.FlatSparray(idx, val, shape=shape, is_canonical=True)
+        got = A.transpose(*axes)
+        np.testing.assert_array_equal(got.toarray(), np.transpose(fo.toarray(idx, val, shape), axes))
+        assert_sparse_same(got, fo.transpose(idx, val, shape, axes))
+
+
+def test_transpose_round_trip_property(sp):
+    """Size-independent property: transposing there and back is the identity; values only move."""
+    rng = np.random.default_rng(4)
+    shape = (128, 96, 80, 24)
+    idx, val = rand_operand(rng, shape, 2_000_000, np.float32)
+    A = sp.FlatSparray(idx, val, shape=shape, is_canonical=True)
+    axes = (2, 0, 3, 1)
+    inv = tuple(np.argsort(axes).tolist())
+    B = A.transpose(*axes)
+    bi = to_np(B.indices)
+    assert np.all(np.diff(bi) > 0)
+    assert abs(float(to_np(B.data).astype(np.float64).sum()) - float(val.astype(np.float64).sum())) < 1e-3
+    assert_sparse_same(B.transpose(*inv), (idx, val, shape))
+
+
+def test_reshape_ravel_are_metadata_only(sp):
+    rng = np.random.default_rng(6)
+    idx, val = rand_operand(rng, (30, 40, 50), 5000, np.float64)
+    A = sp.FlatSparray(idx, val, shape=(30, 40, 50), is_canonical=True)
+    B = A.reshape((1200, 50))
+    assert B.indices.data_ptr() == A.indices.data_ptr() and B.data.data_ptr() == A.data.data_ptr()
+    assert A.reshape((-1, 100)).shape == (600, 100)
+    assert A.ravel().shape == (60000,)
+    np.testing.assert_array_equal(B.toarray(), fo.toarray(idx, val, (30, 40, 50)).reshape(1200, 50))
+    # config 3's "reshape then .T": metadata reshape followed by a real re-sort
+    got = B.T
+    assert_sparse_same(got, fo.transpose(idx, val, (1200, 50), None))
+
+
+@pytest.mark.parametrize("shape,nnz", SHAPES)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64, np.int32], ids=lambda d: np.dtype(d).name)
+def test_sum_axis_random(sp, shape, nnz, dtype):
+    rng = np.random.default_rng(len(shape) * 77 + nnz)
+    idx, val = rand_operand(rng, shape, nnz, dtype)
+    A = sp.FlatSparray(idx, val, shape=shape, is_canonical=True)
+    for axis in range(len(shape)):
+        got = A.sum(axis=axis)
+        want = fo.sum_axis(idx, val, shape, axis)
+        assert got.dtype == np.float64
+        assert_sparse_same(got, want, exact=False, rtol=RTOL[np.dtype(dtype)])
+    total = A.sum()
+    np.testing.assert_allclose(float(total), float(val.astype(np.float64).sum()), rtol=1e-5 if dtype == np.float32 else 1e-12)
+    got = A.mean(axis=0)
+    want = fo.mean_axis(idx, val, shape, 0)
+    assert_sparse_same(got, want, exact=False, rtol=RTOL[np.dtype(dtype)])
+
+
+def test_sum_axis_long_segments(sp):
+    """Segments far longer than a tile (carry crosses many tiles) and all-equal keys."""
+    rng = np.random.default_rng(8)
+    shape = (3, 200000)
+    idx, val = rand_operand(rng, shape, 500000, np.float64)
+    A = sp.FlatSparray(idx, val, shape=shape, is_canonical=True)
+    assert_sparse_same(A.sum(axis=1), fo.sum_axis(idx, val, shape, 1), exact=False, rtol=1e-12)
+    assert_sparse_same(A.sum(axis=0), fo.sum_axis(idx, val, shape, 0), exact=False, rtol=1e-12)
+    shape = (1, 10 ** 6)
+    idx, val = rand_operand(rng, shape, 300000, np.float32)
+    A = sp.FlatSparray(idx, val, shape=shape, is_canonical=True)
+    assert_sparse_same(A.sum(axis=1), fo.sum_axis(idx, val, shape, 1), exact=False, rtol=1e-5)
+
+
+def test_config2_chain(sp):
+    """BASELINE config 2 at full size: c = a*b (intersection) then c.sum(axis=2); also a.sum(axis=2)."""
+    shape = (256, 256, 256, 64)
+    ai, av = fo.random_operand(shape, 0.01, np.float32, 1)
+    bi, bv = fo.random_operand(shape, 0.01, np.float32, 2)
+    A = sp.FlatSparray(ai, av, shape=shape, is_canonical=True)
+    B = sp.FlatSparray(bi, bv, shape=shape, is_canonical=True)
+    C = A * B
+    ci, cv = fo.pairwise_intersect(ai, av, bi, bv, np.multiply)
+    assert_sparse_same(C, (ci, cv, shape))
+    assert_sparse_same(C.sum(axis=2), fo.sum_axis(ci, cv, shape, 2), exact=False, rtol=1e-5)
+    assert_sparse_same(A.sum(axis=2), fo.sum_axis(ai, av, shape, 2), exact=False, rtol=1e-5)
+    assert_sparse_same(A.sum(axis=3), fo.sum_axis(ai, av, shape, 3), exact=False, rtol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=lambda d: np.dtype(d).name)
+def test_spmv_random(sp, dtype):
+    rng = np.random.default_rng(12)
+    rtol = RTOL[np.dtype(dtype)]
+    for shape, nnz in [((2000, 3000), 200000), ((50, 40, 600), 100000), ((1, 5000), 2000), ((10 ** 5, 10 ** 5), 10 ** 6)]:
+        idx, val = rand_operand(rng, shape, nnz, dtype)
+        x = rng.standard_normal(shape[-1]).astype(dtype)
+        A = sp.FlatSparray(idx, val, shape=shape, is_canonical=True)
+        got = A.dot(x)
+        want = fo.dot_dense_vector(idx, val, shape, x)
+        assert isinstance(got, np.ndarray) and got.dtype == want.dtype and got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=rtol, atol=rtol * np.abs(want).max())
+        # sparse-vector operand -> sparse result (flat.py:545-561)
+        xs = x.copy()
+        xs[rng.random(len(xs)) < 0.5] = 0
+        got = A.dot(sp.FlatSparray.from_ndarray(xs))
+        want = fo.dot_dense_vector(idx, val, shape, xs)
+        np.testing.assert_allclose(got.toarray(), want, rtol=rtol, atol=rtol * np.abs(want).max())
+    with pytest.raises(ValueError):
+        A.dot(np.ones(7, dtype=dtype))
+
+
+def test_getitem_random_vs_dense(sp):
+    """The reference's own method: differential test against dense numpy indexing."""
+    rng = np.random.default_rng(14)
+    shape = (23, 17, 29)
+    idx, val = rand_operand(rng, shape, 4000, np.float64)
+    A = sp.FlatSparray(idx, val, shape=shape, is_canonical=True)
+    D = fo.toarray(idx, val, shape)
+    O = fo.OracleSparray(idx, val, shape=shape, is_canonical=True)
+    queries = [(3,), (-1,), (5, 6), (slice(None), 4), (Ellipsis, 7), (2, Ellipsis, 3), (slice(2, 20, 3),),
+               (slice(1, None), slice(None, 9), slice(4, 25, 5)), (slice(5, 6), 3, slice(None)),
+               ([1, 5, 20], [0, 16, 3], [28, 0, 7]), ([20, 5, 1], [0, 16, 3], [28, 0, 7]),
+               ([3, 3, 9],), ([1, 3], slice(None), slice(2, 9)), ([4, 0, 7], 2, slice(None)),
+               (np.arange(23) % 3 == 0,), (slice(None), [16, 2], 5)]
+    for q in queries:
+        got = A[q]
+        want_dense = D[q]
+        np.testing.assert_array_equal(got.toarray(), want_dense, err_msg=str(q))
+        gi = to_np(got.indices)
+        assert np.all(np.diff(gi) > 0)
+        cells = np.arange(D.size).reshape(shape)[q].ravel()
+        if len(np.unique(cells)) == len(cells):     # the reference (and so the oracle) is undefined on repeats
+            assert_sparse_same(got, O[q])
+    for q in [(3, 4, 5), (-1, -1, -1), (0, 0, 0), (22, 16, 28)]:
+        assert A[q] == D[q]
+    assert A[...] is A and A[:, :, :] is A
+    with pytest.raises(IndexError):
+        A[23]
+    with pytest.raises(IndexError):
+        A[1, 2, 3, 4]
+
+
+def test_getitem_rows_of_large_matrix(sp):
+    """asv workload shapes (bench/benchmarks/ops.py:19-38): arr[876], arr[:,273], arr[:5,:5], arr[154,145]."""
+    rng = np.random.default_rng(16)
+    shape = (3000, 4000)
+    idx, val = rand_operand(rng, shape, 1_200_000, np.float64)
+    A = sp.FlatSparray(idx, val, shape=shape, is_canonical=True)
+    O = fo.OracleSparray(idx, val, shape=shape, is_canonical=True)
+    for q in [(876,), (slice(None), 273), (slice(None, 5), slice(None, 5)), (slice(100, 2900, 7), slice(3, 3999, 11))]:
+        assert_sparse_same(A[q], O[q])
+    assert A[154, 145] == O[154, 145]
+    assert_sparse_same(A.diagonal(), O[np.arange(3000), np.arange(3000)])
+    assert_sparse_same(A.diagonal(5), O[np.arange(3000), np.arange(3000) + 5])
+    assert_sparse_same(A.diagonal(-7), O[np.arange(2993) + 7, np.arange(2993)])
+
+
+def test_ctor_canonicalises(sp):
+    rng = np.random.default_rng(18)
+    for dtype in (np.float64, np.float32, np.int64):
+        idx = rng.integers(0, 5000, size=40000).astype(np.int64)
+        val = rand_operand(rng, (10 ** 6,), 80000, dtype)[1][:40000]
+        A = sp.FlatSparray(idx, val, shape=(50, 100))
+        wi, wv = fo.canonicalize(idx, val)
+        rt = 1e-5 if dtype == np.float32 else 1e-12
+        assert_sparse_same(A, (wi, wv, (50, 100)), exact=(dtype == np.int64), rtol=rt)
+    A = sp.FlatSparray([4, 1, 3, 0], [2, -1, 1, -2])      # shape inferred (flat.py:36-37)
+    assert A.shape == (5,)
+    np.testing.assert_array_equal(A.toarray(), [-2, -1, 0, 1, 2])
+
+
+def test_converters_and_unary(sp):
+    rng = np.random.default_rng(20)
+    D = rng.standard_normal((40, 50, 6))
+    D[rng.random(D.shape) < 0.8] = 0
+    A = sp.FlatSparray.from_ndarray(D)
+    wi, wv, _ = fo.from_ndarray(D)
+    assert_sparse_same(A, (wi, wv, D.shape))
+    np.testing.assert_array_equal(A.toarray(), D)
+    np.testing.assert_array_equal((-A).toarray(), -D)
+    np.testing.assert_array_equal(abs(A).toarray(), abs(D))
+    np.testing.assert_array_equal((A * 2.5).toarray(), D * 2.5)
+    np.testing.assert_array_equal((3 * A).toarray(), 3 * D)
+    np.testing.assert_array_equal((A / 4).toarray(), D * (1. / 4))
+    np.testing.assert_array_equal((A ** 2).toarray(), D ** 2)
+    np.testing.assert_array_equal((A > 0.5).toarray(), D > 0.5)
+    np.testing.assert_array_equal(A.astype(np.float32).toarray(), D.astype(np.float32))
+    np.testing.assert_allclose(A.sin().toarray(), np.sin(D), rtol=1e-15, atol=1e-16)
+    assert A.min() == wv.min() and A.max() == wv.max()
+    assert A.nnz == len(wi) and A.dtype == np.float64 and len(A) == 40
+    nz = A.nonzero()
+    for g, w in zip(nz, np.nonzero(D)):
+        np.testing.assert_array_equal(g, w)
+    import scipy.sparse as ss
+    M = ss.random(60, 70, density=0.2, format="csr", random_state=3)
+    S = sp.FlatSparray.from_spmatrix(M)
+    np.testing.assert_array_equal(S.toarray(), M.toarray())
+    np.testing.assert_array_equal(S.tocoo().toarray(), M.toarray())
+    B = A.copy()
+    B *= 2
+    np.testing.assert_array_equal(B.toarray(), D * 2)
+    assert sp.is_sparray(A) and not sp.is_sparray(D)
+    with pytest.raises(NotImplementedError):
+        A += A
