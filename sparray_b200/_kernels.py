@@ -86,10 +86,18 @@ def len_range(start, stop, step):
 
 # ---- section 2: fused sparse (op) sparse ----------------------------------------------------
 
+_WIDEN = {torch.bool: torch.int32, torch.uint8: torch.int32, torch.int8: torch.int32, torch.int16: torch.int32}
+
+
 def setop_binop(kind, op, a_idx, a_val, b_idx, b_val):
-    """kind: 'union' | 'intersect'.  Values must already share a dtype."""
+    """kind: 'union' | 'intersect'.  Values must already share a dtype.  The fused kernels
+    are instantiated for 4- and 8-byte values; bool / 8- / 16-bit operands are widened to
+    int32 for the merge and narrowed back (bool: + is OR, * is AND, as in numpy)."""
     require_cuda()
     assert a_val.dtype == b_val.dtype
+    orig = a_val.dtype
+    if orig in _WIDEN:
+        a_val, b_val = cast(a_val, _WIDEN[orig]), cast(b_val, _WIDEN[orig])
     na, nb = a_idx.numel(), b_idx.numel()
     cap = na + nb if kind == "union" else min(na, nb)
     out_dtype = torch.bool if op in dt.COMPARISONS else a_val.dtype
@@ -100,7 +108,10 @@ def setop_binop(kind, op, a_idx, a_val, b_idx, b_val):
     check(fn(dt.BINOPS[op], dt.spb_dtype(a_val.dtype), ptr(a_idx), ptr(a_val), na, ptr(b_idx), ptr(b_val), nb,
              ptr(out_idx), ptr(out_val), ptr(cnt), workspace(), stream()))
     n = _count(cnt)
-    return out_idx[:n], out_val[:n]
+    out_idx, out_val = out_idx[:n], out_val[:n]
+    if orig in _WIDEN and op not in dt.COMPARISONS:
+        out_val = cast(out_val, orig)
+    return out_idx, out_val
 
 
 # ---- section 3: maps, conversion, lookup -----------------------------------------------------

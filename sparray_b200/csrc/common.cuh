@@ -39,9 +39,10 @@ extern unsigned long long g_launches;
 // [kWsMiscBytes, ...) epoch-tagged look-back state words.  Only state words are ever
 // written to the second region, so a stale word can never alias a live epoch.
 constexpr size_t kWsMiscBytes = 1u << 20;
-int workspace_reserve(spb_workspace* ws, size_t state_bytes, cudaStream_t stream);   // setops.cu
+int workspace_reserve(spb_workspace* ws, size_t state_bytes, cudaStream_t stream);   // workspace.cu
 int workspace_next_epoch(spb_workspace* ws, cudaStream_t stream, uint32_t* epoch);
 int workspace_reserve_payload(spb_workspace* ws, size_t bytes, cudaStream_t stream);
+int device_sm_count();
 inline uint64_t* ws_state(spb_workspace* ws) { return reinterpret_cast<uint64_t*>((char*)ws->dev + kWsMiscBytes); }
 inline char* ws_misc(spb_workspace* ws) { return (char*)ws->dev; }
 
@@ -205,6 +206,49 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* state, in
         total += v;
         if (has_prefix) break;
         base -= 32;
+    }
+    return total;
+}
+
+// Block-wide variant for 256-thread CTAs: every thread inspects one predecessor tile, so a
+// whole wave of concurrently running tiles (persistent kernels: a few hundred) is covered in one
+// or two rounds instead of a dozen dependent warp-wide ones.  `scratch` = 20 ints of shared
+// memory.  Must be called by all 256 threads; returns the exclusive prefix in every thread.
+__device__ __forceinline__ uint64_t lookback_exclusive_block256(const uint64_t* state, int64_t tile, uint32_t epoch,
+                                                                int* scratch) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int* s_stop = scratch;                                         // [8] nearest prefix per warp
+    unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(scratch + 8);   // [8] (16-byte aligned scratch)
+    uint64_t total = 0;
+    int64_t base = tile - 1;
+    while (base >= 0) {
+        const int64_t t = base - tid;
+        uint64_t w;
+        if (t >= 0) {
+            for (;;) {
+                w = ld_state(state + t);
+                if ((w >> 62) != 0 && (uint32_t)((w >> 48) & ((1u << kEpochBits) - 1)) == epoch) break;
+                __nanosleep(20);
+            }
+        } else {
+            w = pack_state(kStPrefix, epoch, 0);
+        }
+        const unsigned has_prefix = __ballot_sync(0xffffffffu, (w >> 62) == kStPrefix);
+        if (lane == 0) s_stop[warp] = has_prefix ? warp * 32 + (__ffs(has_prefix) - 1) : 256;
+        __syncthreads();
+        int stop = 256;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) stop = s_stop[i] < stop ? s_stop[i] : stop;
+        uint64_t v = tid <= stop ? (w & kCountMask) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_sum[warp] = v;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) total += s_sum[i];
+        __syncthreads();                                           // scratch is reused by the next round
+        if (stop < 256) break;
+        base -= 256;
     }
     return total;
 }

@@ -1,0 +1,89 @@
+// sparray_b200/csrc/workspace.cu -- per-stream scratch: look-back state words (epoch-tagged,
+// never memset between launches), a small plain scratch slab, and a payload buffer.
+#include "common.cuh"
+
+namespace spb {
+
+int workspace_reserve(spb_workspace* ws, size_t state_bytes, cudaStream_t stream) {
+    if (!ws) return SPB_ERR_BAD_ARG;
+    const size_t bytes = kWsMiscBytes + state_bytes;
+    if (ws->bytes >= bytes && ws->dev) return SPB_OK;
+    size_t want = bytes + state_bytes / 2 + (1u << 20);
+    if (ws->dev) {
+        SPB_CUDA_TRY(cudaStreamSynchronize(stream));
+        SPB_CUDA_TRY(cudaFree(ws->dev));
+        ws->dev = nullptr;
+        ws->bytes = 0;
+    }
+    SPB_CUDA_TRY(cudaMalloc(&ws->dev, want));
+    SPB_CUDA_TRY(cudaMemsetAsync(ws->dev, 0, want, stream));
+    ws->bytes = want;
+    ws->epoch = 0;
+    return SPB_OK;
+}
+
+int workspace_reserve_payload(spb_workspace* ws, size_t bytes, cudaStream_t stream) {
+    if (!ws) return SPB_ERR_BAD_ARG;
+    if (ws->payload_bytes >= bytes && ws->payload) return SPB_OK;
+    if (ws->payload) {
+        SPB_CUDA_TRY(cudaStreamSynchronize(stream));
+        SPB_CUDA_TRY(cudaFree(ws->payload));
+        ws->payload = nullptr;
+        ws->payload_bytes = 0;
+    }
+    const size_t want = bytes + bytes / 2 + (1u << 20);
+    SPB_CUDA_TRY(cudaMalloc(&ws->payload, want));
+    ws->payload_bytes = want;
+    return SPB_OK;
+}
+
+// next launch epoch (1 .. 2^14-1); re-zero the state words when the counter wraps
+int workspace_next_epoch(spb_workspace* ws, cudaStream_t stream, uint32_t* epoch) {
+    ws->epoch += 1;
+    if (ws->epoch >= (1u << kEpochBits)) {
+        SPB_CUDA_TRY(cudaMemsetAsync(ws->dev, 0, ws->bytes, stream));
+        ws->epoch = 1;
+    }
+    *epoch = ws->epoch;
+    return SPB_OK;
+}
+
+int device_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+}  // namespace spb
+
+extern "C" {
+
+int spb_workspace_create(spb_workspace** ws) {
+    if (!ws) return SPB_ERR_BAD_ARG;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return SPB_ERR_NO_DEVICE;
+    spb_workspace* w = new spb_workspace();
+    w->dev = nullptr;
+    w->bytes = 0;
+    w->epoch = 0;
+    w->device = dev;
+    w->payload = nullptr;
+    w->payload_bytes = 0;
+    *ws = w;
+    return SPB_OK;
+}
+
+int spb_workspace_destroy(spb_workspace* ws) {
+    if (!ws) return SPB_OK;
+    if (ws->dev) cudaFree(ws->dev);
+    if (ws->payload) cudaFree(ws->payload);
+    delete ws;
+    return SPB_OK;
+}
+
+}  // extern "C"
