@@ -1,0 +1,37 @@
+"""Kernel-only timing of the fused setop kernels (CUDA events), optionally under SPB_DEBUG
+elimination flags.  Usage: python profiles/time_setop.py"""
+import os, sys
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import sparray_b200 as sp
+from sparray_b200 import _dtypes as dt
+from sparray_b200._lib import check, lib, ptr, stream, workspace
+sys.path.insert(0, os.path.join(os.path.dirname(__file__)))
+from run_kernels import synth
+
+def main():
+    size = 256 * 256 * 256 * 64
+    ai, av = synth(10_700_000, size, torch.float32, 1)
+    bi, bv = synth(10_700_000, size, torch.float32, 2)
+    na, nb = ai.numel(), bi.numel()
+    out_idx = torch.empty(na + nb, dtype=torch.int64, device="cuda")
+    out_val = torch.empty(na + nb, dtype=torch.float32, device="cuda")
+    cnt = torch.empty(1, dtype=torch.int64, device="cuda")
+    for name, fn, op in (("intersect", lib.spb_intersect_binop, "mul"), ("union", lib.spb_union_binop, "add")):
+        def launch():
+            check(fn(dt.BINOPS[op], dt.SPB_F32, ptr(ai), ptr(av), na, ptr(bi), ptr(bv), nb, ptr(out_idx), ptr(out_val),
+                     ptr(cnt), workspace(), stream()))
+        for _ in range(5):
+            launch()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(20):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); launch(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        print("SPB_DEBUG=%s %s: median %.1f us  min %.1f us  (nout=%d)" % (os.environ.get("SPB_DEBUG", "0"), name,
+              np.median(ts) * 1e3, np.min(ts) * 1e3, int(cnt.item())))
+
+if __name__ == "__main__":
+    main()

@@ -210,6 +210,44 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* state, in
     return total;
 }
 
+// Warp variant that inspects 8 predecessor tiles per lane (256 per round): for persistent
+// kernels whose look-back is deferred until the predecessors' counts are already published,
+// so one round of independent loads normally reaches the previous wave's prefix.
+__device__ __forceinline__ uint64_t lookback_exclusive_wide(const uint64_t* state, int64_t tile, uint32_t epoch) {
+    const int lane = threadIdx.x & 31;
+    uint64_t total = 0;
+    int64_t base = tile - 1;
+    while (base >= 0) {
+        uint64_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t t = base - (lane * 8 + j);
+            w[j] = t >= 0 ? ld_state(state + t) : pack_state(kStPrefix, epoch, 0);
+        }
+        uint64_t part = 0;
+        bool found = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t t = base - (lane * 8 + j);
+            while ((w[j] >> 62) == 0 || (uint32_t)((w[j] >> 48) & ((1u << kEpochBits) - 1)) != epoch) {
+                __nanosleep(20);
+                w[j] = ld_state(state + t);
+            }
+            if (!found) part += w[j] & kCountMask;
+            found = found || (w[j] >> 62) == kStPrefix;
+        }
+        const unsigned has_prefix = __ballot_sync(0xffffffffu, found);
+        const int stop = has_prefix ? (__ffs(has_prefix) - 1) : 31;
+        uint64_t v = lane <= stop ? part : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        total += v;
+        if (has_prefix) break;
+        base -= 256;
+    }
+    return total;
+}
+
 // Block-wide variant for 256-thread CTAs: every thread inspects one predecessor tile, so a
 // whole wave of concurrently running tiles (persistent kernels: a few hundred) is covered in one
 // or two rounds instead of a dozen dependent warp-wide ones.  `scratch` = 20 ints of shared

@@ -30,6 +30,8 @@
 //      No lut / mask array ever exists and nothing is read twice.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace spb {
 
 template <typename V>
@@ -97,10 +99,11 @@ struct SetopParams {
     int64_t* b_pos;
     int64_t* out_count;
     uint64_t* state;     // one look-back word per tile
-    const int64_t* splits;   // [ntiles + 1] merge-path split (A index) of every tile boundary
+    const uint64_t* desc;    // [ntiles][kDescWords] staging descriptors written by the partition kernel
     int64_t ntiles;
     uint32_t epoch;
     int op;
+    int debug;           // SPB_DEBUG experiments (timing only; results are wrong when set)
     int negate_b;        // a - b is evaluated as a + (-b), base.py:45-46: a missing partner is +0, not -0
 };
 
@@ -110,17 +113,91 @@ constexpr int kNT = 256;   // threads per CTA
 constexpr int kVT = 8;     // merged items per thread
 constexpr int kTile = kNT * kVT;
 
-// ---- launch 1: merge-path split of every tile boundary ---------------------------------------
-__global__ void __launch_bounds__(256) merge_partition_kernel(const int64_t* __restrict__ a, int64_t na,
-                                                              const int64_t* __restrict__ b, int64_t nb,
-                                                              int64_t ntiles, int64_t* __restrict__ splits) {
-    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (w > ntiles) return;
-    const int64_t total = na + nb;
-    int64_t d = w * kTile;
-    if (d > total) d = total;
-    const int64_t s = merge_path_warp(a, na, b, nb, d);
-    if ((threadIdx.x & 31) == 0) splits[w] = s;
+// ---- launch 1: merge-path split of every tile + its staging descriptor ------------------------
+// One warp per tile: two 32-ary merge-path searches (the tile's two diagonals), then lane 0
+// works out everything the persistent kernel needs to stage the tile -- so that kernel's
+// prefetching warp only loads 128 bytes and issues the copies.
+//   word 0..4 : the Geom record (a0, b0, an|bn, offA|offB, offAv|offBv)
+//   word 5..8 : 16-byte aligned global source of the TMA copy of A keys, B keys, A values, B values
+//   word 9    : 4 x 16 bit  destination offsets inside the tile buffer
+//   word 10   : 4 x 16 bit  TMA byte counts
+//   word 11   : 4 x (4 bit head count, 4 bit tail count): elements before / after the aligned middle
+constexpr int kDescWords = 16;
+
+struct PartitionParams {
+    const int64_t* a;
+    const int64_t* b;
+    int64_t na, nb;
+    const void* a_val;
+    const void* b_val;
+    int val_esize;           // 0: values are not staged
+    int64_t ntiles;
+    uint64_t* desc;          // [ntiles][kDescWords]
+};
+
+__global__ void __launch_bounds__(256) merge_partition_kernel(const PartitionParams p) {
+    const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (t >= p.ntiles) return;
+    constexpr int kKeyReg = (kTile + 4) * 8 + 128 + kVT * 8;
+    const int64_t total = p.na + p.nb;
+    const int64_t d0 = t * kTile;
+    const int64_t d1 = (d0 + kTile < total) ? d0 + kTile : total;
+    const int64_t a0 = merge_path_warp(p.a, p.na, p.b, p.nb, d0);
+    const int64_t a1 = merge_path_warp(p.a, p.na, p.b, p.nb, d1);
+    if ((threadIdx.x & 31) != 0) return;
+    const int64_t b0 = d0 - a0, b1 = d1 - a1;
+    // indices [x0-1, x1] (one halo key either side), values [x0, x1) (+1 for B: partner of the last A)
+    const int64_t ga_lo = a0 > 0 ? a0 - 1 : 0, ga_hi = a1 < p.na ? a1 + 1 : p.na;
+    const int64_t gb_lo = b0 > 0 ? b0 - 1 : 0, gb_hi = b1 < p.nb ? b1 + 1 : p.nb;
+    StagePlan pl[4];
+    int dst0[4];             // buffer offset that the plan's g_al maps to
+    pl[0] = make_stage_plan(p.a, ga_lo, ga_hi, 8);
+    pl[1] = make_stage_plan(p.b, gb_lo, gb_hi, 8);
+    dst0[0] = 16;                                                     // front pad: slot for index -1
+    dst0[1] = dst0[0] + (int)((pl[0].span_bytes() + 15) & ~15u) + 32; // A's +1 sentinel, B's -1 slot
+    const int E = p.val_esize;
+    int narr = 2;
+    if (E) {
+        narr = 4;
+        pl[2] = make_stage_plan(p.a_val, a0, a1, E);
+        pl[3] = make_stage_plan(p.b_val, b0, gb_hi > b1 ? b1 + 1 : b1, E);
+        dst0[2] = kKeyReg;
+        dst0[3] = dst0[2] + (int)((pl[2].span_bytes() + 15) & ~15u) + 16;
+    }
+    uint64_t* d = p.desc + t * kDescWords;
+    d[0] = (uint64_t)a0;
+    d[1] = (uint64_t)b0;
+    d[2] = (uint64_t)(uint32_t)(a1 - a0) | ((uint64_t)(uint32_t)(b1 - b0) << 32);
+    const int offA = dst0[0] + (int)(pl[0].p_lo - pl[0].g_al) + (int)(a0 - ga_lo) * 8;
+    const int offB = dst0[1] + (int)(pl[1].p_lo - pl[1].g_al) + (int)(b0 - gb_lo) * 8;
+    d[3] = (uint64_t)(uint32_t)offA | ((uint64_t)(uint32_t)offB << 32);
+    int offAv = 0, offBv = 0;
+    if (E) {
+        offAv = dst0[2] + (int)(pl[2].p_lo - pl[2].g_al);
+        offBv = dst0[3] + (int)(pl[3].p_lo - pl[3].g_al);
+    }
+    d[4] = (uint64_t)(uint32_t)offAv | ((uint64_t)(uint32_t)offBv << 32);
+    uint64_t w_dst = 0, w_cnt = 0, w_ht = 0;
+    for (int i = 0; i < 4; ++i) {
+        uint64_t src = 0;
+        if (i < narr) {
+            const StagePlan& s = pl[i];
+            const int es = i < 2 ? 8 : E;
+            const uintptr_t head_end = s.q_lo < s.p_hi ? s.q_lo : s.p_hi;      // == q_lo unless the range is tiny
+            const uintptr_t mid = head_end;                                    // the copy starts here
+            const uint32_t bytes = s.tma_bytes();
+            const uintptr_t tail_lo = mid + bytes;
+            src = (uint64_t)mid;
+            w_dst |= (uint64_t)(uint32_t)(dst0[i] + (int)(mid - s.g_al)) << (16 * i);
+            w_cnt |= (uint64_t)bytes << (16 * i);
+            const uint32_t nh = (uint32_t)((mid - s.p_lo) / es), nt = (uint32_t)((s.p_hi - tail_lo) / es);
+            w_ht |= (uint64_t)(nh | (nt << 4)) << (8 * i);
+        }
+        d[5 + i] = src;
+    }
+    d[9] = w_dst;
+    d[10] = w_cnt;
+    d[11] = w_ht;
 }
 
 // ---- shared-memory layout ------------------------------------------------------------------------
@@ -131,16 +208,15 @@ struct Geom {            // where a staged tile lives inside its buffer
     int offAv, offBv;    // byte offset of Av[0] / Bv[0]
 };
 
-template <int VBYTES, int OUT_KEYS, int OUT_PAYLOAD>   // staged value bytes; staging capacity in bytes
+template <int VBYTES, int NBUF, int OUT_KEYS, int OUT_PAYLOAD>   // staged value bytes; ring depth; staging bytes
 struct Layout {
     static constexpr int kHeader = 256;
     static constexpr int kKeyReg = (kTile + 4) * 8 + 128 + kVT * 8;
     static constexpr int kValReg = VBYTES ? kTile * VBYTES + 96 : 0;
-    static constexpr int kBuf = kKeyReg + kValReg;                       // the staged input tile
-    static constexpr int kK32 = ((kTile + 2 * kVT + 24) * 4 + 15) & ~15; // re-based 32-bit keys
+    static constexpr int kBuf = kKeyReg + kValReg;                       // one staged input tile
     static constexpr int kStgKeys = OUT_KEYS;                            // compacted outputs waiting for their offset
     static constexpr int kStg = ((OUT_KEYS + OUT_PAYLOAD) + 15) & ~15;
-    static constexpr int kTotal = kHeader + kBuf + kK32 + kStg;
+    static constexpr int kTotal = kHeader + NBUF * kBuf + kStg;
     static_assert(kKeyReg % 16 == 0 && kValReg % 16 == 0, "buffers must stay 16-byte aligned for TMA");
 };
 
@@ -150,7 +226,10 @@ struct Cfg {
     static constexpr int kCap = KIND == KIND_UNION ? kTile : kTile / 2;  // outputs per tile, at most
     static constexpr int kPayload = HAS_VAL ? kCap * (int)sizeof(VO)
                                             : (SEAM ? (KIND == KIND_UNION ? kCap : 2 * kCap * 8) : 0);
-    using L = Layout<kStageVals ? (int)sizeof(V) : 0, kCap * 8, kPayload>;
+    // tiles in flight per CTA: enough bytes on the wire per SM to cover HBM latency (Little's law)
+    static constexpr int kNBuf = (kStageVals && sizeof(V) == 8) ? 2 : 3;
+    static constexpr int kMinCtas = kStageVals ? 2 : 3;
+    using L = Layout<kStageVals ? (int)sizeof(V) : 0, kNBuf, kCap * 8, kPayload>;
 };
 
 struct EdgeReg {         // an unaligned head / tail element riding in a register until its buffer is live
@@ -159,22 +238,6 @@ struct EdgeReg {         // an unaligned head / tail element riding in a registe
     uint32_t size;
 };
 
-__device__ __forceinline__ void edge_load(EdgeReg& er, const StagePlan& s, char* buf, int esize, bool tail, int j) {
-    const uintptr_t head_end = s.q_lo < s.p_hi ? s.q_lo : s.p_hi;
-    uintptr_t lo = s.p_lo, hi = head_end;
-    if (tail) {
-        lo = s.q_hi > head_end ? s.q_hi : head_end;
-        hi = s.p_hi;
-    }
-    const uintptr_t addr = lo + (uintptr_t)j * esize;
-    if (addr < hi) {
-        er.dst = smem_u32(buf + (addr - s.g_al));
-        er.size = (uint32_t)esize;
-        if (esize == 8) er.raw = __ldg(reinterpret_cast<const unsigned long long*>(addr));
-        else er.raw = __ldg(reinterpret_cast<const unsigned int*>(addr));
-    }
-}
-
 __device__ __forceinline__ void edge_store(const EdgeReg& er) {
     if (er.dst) {
         if (er.size == 8) asm volatile("st.shared.u64 [%0], %1;" ::"r"(er.dst), "l"(er.raw) : "memory");
@@ -182,75 +245,73 @@ __device__ __forceinline__ void edge_store(const EdgeReg& er) {
     }
 }
 
-// Executed by the whole of warp 0: stage tile `tile` into `buf` (TMA for the aligned middle,
-// registers for the ragged edges), describe it in *g.
-template <typename V, bool STAGE_VALS>
-__device__ __forceinline__ void prefetch_tile(const SetopParams& p, int64_t tile, char* buf, uint64_t* bar, Geom* g,
-                                              EdgeReg& er, int lane) {
-    constexpr int kKeyReg = (kTile + 4) * 8 + 128 + kVT * 8;
-    const int64_t total = p.na + p.nb;
-    const int64_t a0 = __ldg(p.splits + tile), a1 = __ldg(p.splits + tile + 1);
-    const int64_t d0 = tile * kTile;
-    const int64_t d1 = (d0 + kTile < total) ? d0 + kTile : total;
-    const int64_t b0 = d0 - a0, b1 = d1 - a1;
-    // indices [x0-1, x1] (one halo key either side), values [x0, x1) (+1 for B: partner of the last A)
-    const int64_t ga_lo = a0 > 0 ? a0 - 1 : 0, ga_hi = a1 < p.na ? a1 + 1 : p.na;
-    const int64_t gb_lo = b0 > 0 ? b0 - 1 : 0, gb_hi = b1 < p.nb ? b1 + 1 : p.nb;
-    const StagePlan pa = make_stage_plan(p.a, ga_lo, ga_hi, 8);
-    const StagePlan pb = make_stage_plan(p.b, gb_lo, gb_hi, 8);
-    char* bufA = buf + 16;                                            // front pad: slot for index -1
-    char* bufB = bufA + ((pa.span_bytes() + 15) & ~15u) + 32;         // A's +1 sentinel, B's -1 slot
-    StagePlan pav{}, pbv{};
-    char *bufAv = buf + kKeyReg, *bufBv = nullptr;
-    if constexpr (STAGE_VALS) {
-        pav = make_stage_plan(p.a_val, a0, a1, sizeof(V));
-        pbv = make_stage_plan(p.b_val, b0, gb_hi > b1 ? b1 + 1 : b1, sizeof(V));
-        bufBv = bufAv + ((pav.span_bytes() + 15) & ~15u) + 16;
+// Executed by the whole of warp 0: put one tile in flight.  `dw` is this lane's word of the
+// tile descriptor (lanes 0..15).  Lanes 0..3 each issue one TMA bulk copy, lanes 16..31 each
+// pick up one ragged-edge element in a register, lanes 0..4 publish the geometry.
+template <int VBYTES>
+__device__ __forceinline__ void prefetch_tile(uint64_t dw, char* buf, uint64_t* bar, Geom* g, EdgeReg& er, int lane) {
+    if (lane < 5) reinterpret_cast<uint64_t*>(g)[lane] = dw;
+    const uint64_t w_dst = __shfl_sync(0xffffffffu, dw, 9);
+    const uint64_t w_cnt = __shfl_sync(0xffffffffu, dw, 10);
+    const uint32_t w_ht = (uint32_t)__shfl_sync(0xffffffffu, dw, 11);
+    // which array this lane serves: TMA lanes by index, edge lanes by slot
+    const int s = lane - 16;                                          // edge slot 0..15
+    int arr = lane & 3;
+    int tail = 0, j = 0;
+    if (lane >= 16) {
+        arr = s < 2 ? 0 : (s < 4 ? 1 : (s < 10 ? 2 : 3));
+        const int r = s < 4 ? 0 : (s - 4) % 6;
+        tail = s < 4 ? (s & 1) : (r >= 3);
+        j = s < 4 ? 0 : r % 3;
     }
+    const uint64_t src = __shfl_sync(0xffffffffu, dw, 5 + arr);
+    const uint32_t dst = (uint32_t)(w_dst >> (16 * arr)) & 0xffffu;
+    const uint32_t bytes = (uint32_t)(w_cnt >> (16 * arr)) & 0xffffu;
     if (lane == 0) {
-        g->a0 = a0;
-        g->b0 = b0;
-        g->an = (int)(a1 - a0);
-        g->bn = (int)(b1 - b0);
-        g->offA = (int)(bufA - buf) + (int)(pa.p_lo - pa.g_al) + (int)(a0 - ga_lo) * 8;
-        g->offB = (int)(bufB - buf) + (int)(pb.p_lo - pb.g_al) + (int)(b0 - gb_lo) * 8;
-        uint32_t bytes = pa.tma_bytes() + pb.tma_bytes();
-        if constexpr (STAGE_VALS) {
-            g->offAv = (int)(bufAv - buf) + (int)(pav.p_lo - pav.g_al);
-            g->offBv = (int)(bufBv - buf) + (int)(pbv.p_lo - pbv.g_al);
-            bytes += pav.tma_bytes() + pbv.tma_bytes();
-        }
-        mbar_arrive_expect_tx(bar, bytes);
-        stage_issue_tma(pa, bufA, bar);
-        stage_issue_tma(pb, bufB, bar);
-        if constexpr (STAGE_VALS) {
-            stage_issue_tma(pav, bufAv, bar);
-            stage_issue_tma(pbv, bufBv, bar);
-        }
+        const uint32_t total = (uint32_t)(w_cnt & 0xffffu) + (uint32_t)((w_cnt >> 16) & 0xffffu) +
+                               (uint32_t)((w_cnt >> 32) & 0xffffu) + (uint32_t)((w_cnt >> 48) & 0xffffu);
+        mbar_arrive_expect_tx(bar, total);
     }
+    __syncwarp();
+    if (lane < 4 && bytes) tma_bulk_g2s(buf + dst, reinterpret_cast<const void*>(src), bytes, bar);
     er.dst = 0;
     er.size = 0;
     er.raw = 0;
-    if (lane == 1) edge_load(er, pa, bufA, 8, false, 0);
-    else if (lane == 2) edge_load(er, pa, bufA, 8, true, 0);
-    else if (lane == 3) edge_load(er, pb, bufB, 8, false, 0);
-    else if (lane == 4) edge_load(er, pb, bufB, 8, true, 0);
-    if constexpr (STAGE_VALS) {
-        constexpr int E = (int)sizeof(V);
-        if (lane >= 5 && lane <= 7) edge_load(er, pav, bufAv, E, false, lane - 5);
-        else if (lane >= 8 && lane <= 10) edge_load(er, pav, bufAv, E, true, lane - 8);
-        else if (lane >= 11 && lane <= 13) edge_load(er, pbv, bufBv, E, false, lane - 11);
-        else if (lane >= 14 && lane <= 16) edge_load(er, pbv, bufBv, E, true, lane - 14);
+    if (lane >= 16 && src) {
+        const int E = arr < 2 ? 8 : VBYTES;
+        const int nh = (int)(w_ht >> (8 * arr)) & 15, nt = (int)(w_ht >> (8 * arr + 4)) & 15;
+        const int n = tail ? nt : nh;
+        if (E && j < n) {
+            const int64_t delta = tail ? (int64_t)bytes + (int64_t)j * E : -(int64_t)(nh - j) * E;
+            const uintptr_t addr = (uintptr_t)((int64_t)src + delta);
+            er.dst = smem_u32(buf + dst) + (uint32_t)(int32_t)delta;
+            er.size = (uint32_t)E;
+            if (E == 8) er.raw = __ldg(reinterpret_cast<const unsigned long long*>(addr));
+            else er.raw = __ldg(reinterpret_cast<const unsigned int*>(addr));
+        }
     }
 }
 
-template <typename K>
-__device__ __forceinline__ int merge_path_smem(const K* a, int na, const K* b, int nb, int d) {
+// Key accessors over the staged int64 keys.  When a tile's keys span less than 2^32 the merge
+// runs on single-register keys: the low word of each key minus the low word of the tile's
+// smallest key (exact modulo 2^32 because the true offset fits 32 bits).
+struct NarrowKeys {
+    const uint32_t* w;       // low word of element 0 (little endian); element i is w[2 * i]
+    uint32_t base;
+    __device__ __forceinline__ uint32_t operator()(int i) const { return w[2 * i] - base; }
+};
+struct WideKeys {
+    const int64_t* p;
+    __device__ __forceinline__ int64_t operator()(int i) const { return p[i]; }
+};
+
+template <typename Acc>
+__device__ __forceinline__ int merge_path_smem(const Acc& a, int na, const Acc& b, int nb, int d) {
     int lo = d > nb ? d - nb : 0;
     int hi = d < na ? d : na;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (a[mid] <= b[d - 1 - mid]) lo = mid + 1;
+        if (a(mid) <= b(d - 1 - mid)) lo = mid + 1;
         else hi = mid;
     }
     return lo;
@@ -259,42 +320,45 @@ __device__ __forceinline__ int merge_path_smem(const K* a, int na, const K* b, i
 // Branch-free walk of kVT merged items starting at (ai, bi): records who was taken (A or B),
 // where both sides held the same key, and which items are emitted.  Ties go to A; the B
 // partner of a matched A item is the very next item and is suppressed (prev_eq).
-template <typename K, int KIND>
-__device__ __forceinline__ void merge_walk(const K* KA, const K* KB, int ai, int bi, int steps, bool prev_eq,
+template <typename Acc, int KIND>
+__device__ __forceinline__ void merge_walk(const Acc& A, const Acc& B, int ai, int bi, int steps, bool prev_eq,
                                            unsigned& m_ta, unsigned& m_eq, unsigned& m_emit) {
-    K ka = KA[ai], kb = KB[bi];
+    auto ka = A(ai);
+    auto kb = B(bi);
     m_ta = m_eq = m_emit = 0;
 #pragma unroll
     for (int k = 0; k < kVT; ++k) {
         const bool ta = ka <= kb;
         const bool eq = ka == kb;
-        const bool e = KIND == KIND_UNION ? (ta || !prev_eq) : eq;
-        prev_eq = ta && eq;
-        const bool live = k < steps;
-        m_ta |= (unsigned)(ta && live) << k;
-        m_eq |= (unsigned)(eq && ta && live) << k;
-        m_emit |= (unsigned)(e && (ta || KIND == KIND_UNION) && live) << k;
+        m_ta |= (unsigned)ta << k;
+        m_eq |= (unsigned)eq << k;
+        if (KIND == KIND_UNION) m_emit |= (unsigned)(ta || !prev_eq) << k;
+        prev_eq = eq;                     // eq implies ta
         ai += ta ? 1 : 0;
         bi += ta ? 0 : 1;
-        const K kn = ta ? KA[ai] : KB[bi];
+        const auto kn = ta ? A(ai) : B(bi);
         ka = ta ? kn : ka;
         kb = ta ? kb : kn;
     }
+    const unsigned live = steps >= kVT ? (1u << kVT) - 1u : (1u << steps) - 1u;
+    m_ta &= live;
+    m_eq &= live;
+    m_emit = (KIND == KIND_UNION ? m_emit : m_eq) & live;
 }
 
 template <typename V, typename VO, int KIND, bool HAS_VAL, bool SEAM>
-__global__ void __launch_bounds__(kNT, 3) setop_kernel(const SetopParams p) {
+__global__ void __launch_bounds__(kNT, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMinCtas) setop_kernel(const SetopParams p) {
     using C = Cfg<V, VO, KIND, HAS_VAL, SEAM>;
     using L = typename C::L;
     constexpr bool STAGE_VALS = C::kStageVals;
+    constexpr int NBUF = C::kNBuf;
     extern __shared__ __align__(128) char smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                 // mbarrier of the input buffer
-    Geom* geom = reinterpret_cast<Geom*>(smem + 16);
-    int* warp_sums = reinterpret_cast<int*>(smem + 112);                // [8]
-    int* lb_scratch = reinterpret_cast<int*>(smem + 144);               // [8] ints + [8] u64
-    char* buf = smem + L::kHeader;
-    uint32_t* k32 = reinterpret_cast<uint32_t*>(buf + L::kBuf);
-    char* stg = buf + L::kBuf + L::kK32;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                 // [NBUF] one mbarrier per ring slot
+    Geom* geom = reinterpret_cast<Geom*>(smem + 32);                    // [NBUF] (40 bytes each)
+    int* warp_sums = reinterpret_cast<int*>(smem + 160);                // [8]
+    int64_t* base_s = reinterpret_cast<int64_t*>(smem + 192);
+    char* bufs = smem + L::kHeader;
+    char* stg = bufs + NBUF * L::kBuf;
     // compacted outputs of the PREVIOUS tile wait here for their global offset
     int64_t* skey = reinterpret_cast<int64_t*>(stg);
     VO* sval = reinterpret_cast<VO*>(stg + L::kStgKeys);
@@ -304,32 +368,38 @@ __global__ void __launch_bounds__(kNT, 3) setop_kernel(const SetopParams p) {
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int64_t total_items = p.na + p.nb;
     const int64_t stride = gridDim.x;
 
     if (tid == 0) {
-        mbar_init(full, 1);
+        for (int j = 0; j < NBUF; ++j) mbar_init(&full[j], 1);
         fence_mbar_init();
     }
     __syncthreads();
 
+    // ---- prologue: fill the ring ------------------------------------------------------------------
     EdgeReg er{0, 0, 0};
-    int64_t tile = blockIdx.x;
-    if (warp == 0 && tile < p.ntiles) prefetch_tile<V, STAGE_VALS>(p, tile, buf, full, geom, er, lane);
-    uint32_t phase = 0;
+    uint64_t dw_next = 0;                // warp 0: descriptor word of the tile that refills a slot next
+    constexpr int VB = STAGE_VALS ? (int)sizeof(V) : 0;
+    if (warp == 0) {
+        for (int j = 0; j < NBUF; ++j) {
+            const int64_t t = blockIdx.x + j * stride;
+            if (t < p.ntiles) {
+                const uint64_t dw = lane < kDescWords ? __ldg(p.desc + t * kDescWords + lane) : 0;
+                prefetch_tile<VB>(dw, bufs + j * L::kBuf, &full[j], &geom[j], er, lane);
+                edge_store(er);
+            }
+        }
+        er.dst = 0;
+        const int64_t t = blockIdx.x + NBUF * stride;
+        if (t < p.ntiles && lane < kDescWords) dw_next = __ldg(p.desc + t * kDescWords + lane);
+    }
+    uint32_t phase_bits = 0;
     int64_t prev_tile = -1;      // tile whose outputs sit in the staging area
     int prev_total = 0;
+    int slot = 0;
 
-    // Store the staged outputs of `prev_tile`: its predecessors published their counts at least
-    // one tile-iteration ago, so the look-back does not wait.
-    auto flush_prev = [&]() {
-        uint64_t base = 0;
-        if (prev_tile > 0) {
-            base = lookback_exclusive_block256(p.state, prev_tile, p.epoch, lb_scratch);
-            if (tid == 0) st_state(p.state + prev_tile, pack_state(kStPrefix, p.epoch, base + (uint64_t)prev_total));
-        }
-        if (tid == 0 && prev_tile == p.ntiles - 1) *p.out_count = (int64_t)base + prev_total;
-        for (int i = tid; i < prev_total; i += kNT) {
+    auto store_prev = [&](int64_t base) {
+        for (int i = tid; i < ((p.debug & 4) ? 0 : prev_total); i += kNT) {
             if constexpr (SEAM && KIND == KIND_INTERSECT) {
                 p.out_idx[base + i] = skey[i];
                 if (p.a_pos) p.a_pos[base + i] = spa[i];
@@ -343,53 +413,52 @@ __global__ void __launch_bounds__(kNT, 3) setop_kernel(const SetopParams p) {
             }
         }
     };
-
-    for (; tile < p.ntiles; tile += stride) {
-        if (warp == 0) {
-            edge_store(er);                                            // ragged edges of the current tile
-            __syncwarp();                                              // lane 0 wrote *geom when it prefetched
-            int64_t* As64w = reinterpret_cast<int64_t*>(buf + geom->offA);
-            int64_t* Bs64w = reinterpret_cast<int64_t*>(buf + geom->offB);
-            if (lane == 17 && geom->a0 == 0) As64w[-1] = kKeyMin;
-            if (lane == 18 && geom->a0 + geom->an == p.na) As64w[geom->an] = kKeyMax;
-            if (lane == 19 && geom->b0 == 0) Bs64w[-1] = kKeyMin;
-            if (lane == 20 && geom->b0 + geom->bn == p.nb) Bs64w[geom->bn] = kKeyMax;
+    // warp 0: global offset of the staged tile.  Its predecessors published their counts about one
+    // tile-iteration ago, so this normally does not wait.
+    auto lookback_prev = [&]() {
+        const uint64_t b = (prev_tile > 0 && !(p.debug & 1)) ? lookback_exclusive_wide(p.state, prev_tile, p.epoch) : 0;
+        if (lane == 0) {
+            if (prev_tile > 0) st_state(p.state + prev_tile, pack_state(kStPrefix, p.epoch, b + (uint64_t)prev_total));
+            if (prev_tile == p.ntiles - 1) *p.out_count = (int64_t)b + prev_total;
+            *base_s = (int64_t)b;
         }
-        mbar_wait(full, phase);
-        phase ^= 1u;
-        __syncthreads();                                               // (A) tile, edges, sentinels, geometry visible
+    };
 
-        const Geom g = *geom;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += stride) {
+        char* buf = bufs + slot * L::kBuf;
+        Geom* gs = &geom[slot];
+        if (warp == 0) {
+            edge_store(er);                                            // ragged edges of the tile prefetched last
+            er.dst = 0;
+            __syncwarp();                                              // lane 0 wrote the geometry when it prefetched
+            int64_t* As64w = reinterpret_cast<int64_t*>(buf + gs->offA);
+            int64_t* Bs64w = reinterpret_cast<int64_t*>(buf + gs->offB);
+            if (lane == 17 && gs->a0 == 0) As64w[-1] = kKeyMin;
+            if (lane == 18 && gs->a0 + gs->an == p.na) As64w[gs->an] = kKeyMax;
+            if (lane == 19 && gs->b0 == 0) Bs64w[-1] = kKeyMin;
+            if (lane == 20 && gs->b0 + gs->bn == p.nb) Bs64w[gs->bn] = kKeyMax;
+        }
+        mbar_wait(&full[slot], (phase_bits >> slot) & 1u);
+        phase_bits ^= 1u << slot;
+        __syncthreads();                                               // (A) tile, edges, sentinels, geometry, base
+
+        const Geom g = *gs;
         const int an = g.an, bn = g.bn, items = an + bn;
         const int64_t* As64 = reinterpret_cast<const int64_t*>(buf + g.offA);
         const int64_t* Bs64 = reinterpret_cast<const int64_t*>(buf + g.offB);
 
-        // ---- re-base the keys to 32-bit tile-local offsets when the span allows it -----------
+        // ---- 32-bit tile-local keys when the span allows it ---------------------------------------
         const int64_t first_a = an ? As64[0] : kKeyMax, first_b = bn ? Bs64[0] : kKeyMax;
         const int64_t last_a = an ? As64[an - 1] : kKeyMin, last_b = bn ? Bs64[bn - 1] : kKeyMin;
         const int64_t kbase = first_a < first_b ? first_a : first_b;
         const int64_t kmax = last_a > last_b ? last_a : last_b;
         const bool narrow = (uint64_t)(kmax - kbase) < 0xfffffffeull;
         const bool front_dup = bn > 0 && As64[-1] == Bs64[0];          // A's last key of the previous tile pairs B's first
-        uint32_t* KA32 = k32;
-        uint32_t* KB32 = k32 + an + kVT + 4;
-        if (narrow) {
-            for (int e = tid; e <= an + kVT + 1; e += kNT) {
-                uint32_t v = 0xffffffffu;
-                if (e <= an) {
-                    const uint64_t dlt = (uint64_t)(As64[e] - kbase);
-                    v = dlt > 0xfffffffeull ? 0xffffffffu : (uint32_t)dlt;
-                }
-                KA32[e] = v;
-            }
-            for (int e = tid; e <= bn + kVT + 1; e += kNT) {
-                uint32_t v = 0xffffffffu;
-                if (e <= bn) {
-                    const uint64_t dlt = (uint64_t)(Bs64[e] - kbase);
-                    v = dlt > 0xfffffffeull ? 0xffffffffu : (uint32_t)dlt;
-                }
-                KB32[e] = v;
-            }
+        if (narrow && tid < 2) {
+            // the halo / sentinel key behind each range may lie beyond the 32-bit window: clamp it to the
+            // largest offset, which no key of the tile can reach
+            int64_t* h = const_cast<int64_t*>(tid == 0 ? As64 + an : Bs64 + bn);
+            if ((uint64_t)(*h - kbase) > 0xfffffffeull) *h = kbase + 0xffffffffll;
         }
         __syncthreads();                                               // (B)
 
@@ -399,16 +468,21 @@ __global__ void __launch_bounds__(kNT, 3) setop_kernel(const SetopParams p) {
         const int steps = (items - diag) < kVT ? (items - diag) : kVT;
         int ai0, bi0;
         unsigned m_ta, m_eq, m_emit;
-        if (narrow) {
-            ai0 = merge_path_smem<uint32_t>(KA32, an, KB32, bn, diag);
+        if (p.debug & 2) {
+            ai0 = diag / 2; bi0 = diag - ai0; m_ta = 0x55; m_eq = 0; m_emit = KIND == KIND_UNION ? 0xff : 0;
+        } else if (narrow) {
+            const NarrowKeys A{reinterpret_cast<const uint32_t*>(As64), (uint32_t)kbase};
+            const NarrowKeys B{reinterpret_cast<const uint32_t*>(Bs64), (uint32_t)kbase};
+            ai0 = merge_path_smem(A, an, B, bn, diag);
             bi0 = diag - ai0;
-            const bool prev_eq = ai0 > 0 ? (KA32[ai0 - 1] == KB32[bi0]) : (bi0 == 0 && front_dup);
-            merge_walk<uint32_t, KIND>(KA32, KB32, ai0, bi0, steps, prev_eq, m_ta, m_eq, m_emit);
+            const bool prev_eq = ai0 > 0 ? (A(ai0 - 1) == B(bi0)) : (bi0 == 0 && front_dup);
+            merge_walk<NarrowKeys, KIND>(A, B, ai0, bi0, steps, prev_eq, m_ta, m_eq, m_emit);
         } else {
-            ai0 = merge_path_smem<int64_t>(As64, an, Bs64, bn, diag);
+            const WideKeys A{As64}, B{Bs64};
+            ai0 = merge_path_smem(A, an, B, bn, diag);
             bi0 = diag - ai0;
-            const bool prev_eq = ai0 > 0 ? (As64[ai0 - 1] == Bs64[bi0]) : (bi0 == 0 && front_dup);
-            merge_walk<int64_t, KIND>(As64, Bs64, ai0, bi0, steps, prev_eq, m_ta, m_eq, m_emit);
+            const bool prev_eq = ai0 > 0 ? (A(ai0 - 1) == B(bi0)) : (bi0 == 0 && front_dup);
+            merge_walk<WideKeys, KIND>(A, B, ai0, bi0, steps, prev_eq, m_ta, m_eq, m_emit);
         }
 
         // ---- block exclusive scan of the output counts -------------------------------------------
@@ -433,9 +507,9 @@ __global__ void __launch_bounds__(kNT, 3) setop_kernel(const SetopParams p) {
             int ai = ai0, bi = bi0;
 #pragma unroll
             for (int k = 0; k < kVT; ++k) {
-                const bool ta = (m_ta >> k) & 1u, eq = (m_eq >> k) & 1u, e = (m_emit >> k) & 1u;
+                const bool ta = (m_ta >> k) & 1u, eq = ta && ((m_eq >> k) & 1u), e = (m_emit >> k) & 1u;
                 if (e) {
-                    okey[k] = narrow ? kbase + (int64_t)(ta ? KA32[ai] : KB32[bi]) : (ta ? As64[ai] : Bs64[bi]);
+                    okey[k] = ta ? As64[ai] : Bs64[bi];
                     if constexpr (HAS_VAL) {
                         V x, y;
                         if constexpr (STAGE_VALS) {
@@ -468,12 +542,21 @@ __global__ void __launch_bounds__(kNT, 3) setop_kernel(const SetopParams p) {
                 bi += ta ? 0 : ((k < steps) ? 1 : 0);
             }
         }
-        fence_proxy_async_smem();      // my generic reads of the input buffer happen-before the TMA that refills it
+        fence_proxy_async_smem();      // my generic reads of this slot happen-before the TMA that refills it
         __syncthreads();                                               // (C) warp sums ready; the input tile is dead
 
-        // ---- the next tile goes in flight while this one's outputs are handled -------------------
-        if (warp == 0 && tile + stride < p.ntiles)
-            prefetch_tile<V, STAGE_VALS>(p, tile + stride, buf, full, geom, er, lane);
+        // ---- refill this ring slot: kNBuf tiles ahead ------------------------------------------------
+        if (warp == 0) {
+            const int64_t t2 = tile + NBUF * stride;
+            if (t2 < p.ntiles) {
+                prefetch_tile<VB>(dw_next, buf, &full[slot], gs, er, lane);
+                const int64_t t3 = t2 + stride;
+                if (t3 < p.ntiles && lane < kDescWords) dw_next = __ldg(p.desc + t3 * kDescWords + lane);
+            }
+        }
+
+        // ... while warp 1 fetches the global offset of the tile staged one iteration ago
+        if (warp == 1 && prev_tile >= 0) lookback_prev();
 
         int wofs = 0, tile_total = 0;
 #pragma unroll
@@ -487,9 +570,12 @@ __global__ void __launch_bounds__(kNT, 3) setop_kernel(const SetopParams p) {
         if (tid == 0)
             st_state(p.state + tile, pack_state(tile == 0 ? kStPrefix : kStAgg, p.epoch, (uint64_t)tile_total));
 
-        // ---- store the previous tile (its look-back no longer waits), then stage this one -----------
-        if (prev_tile >= 0) flush_prev();
-        __syncthreads();                                               // (D) staging area free
+        // ---- store the previous tile, then stage this one ---------------------------------------------
+        if (prev_tile >= 0) {
+            __syncthreads();                                           // (D) offset of the previous tile visible
+            store_prev(*base_s);
+            __syncthreads();                                           // (E) staging area drained
+        }
 #pragma unroll
         for (int k = 0; k < kVT; ++k) {
             if ((m_emit >> k) & 1u) {
@@ -505,9 +591,14 @@ __global__ void __launch_bounds__(kNT, 3) setop_kernel(const SetopParams p) {
         }
         prev_tile = tile;
         prev_total = tile_total;
+        slot = slot + 1 == NBUF ? 0 : slot + 1;
     }
     __syncthreads();
-    if (prev_tile >= 0) flush_prev();
+    if (prev_tile >= 0) {
+        if (warp == 0) lookback_prev();
+        __syncthreads();
+        store_prev(*base_s);
+    }
 }
 
 template <typename V, typename VO, int KIND, bool HAS_VAL, bool SEAM>
@@ -521,14 +612,17 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
     int rc = workspace_reserve(ws, (size_t)ntiles * sizeof(uint64_t), stream);
     if (rc) return rc;
-    rc = workspace_reserve_payload(ws, (size_t)(ntiles + 1) * sizeof(int64_t), stream);
+    rc = workspace_reserve_payload(ws, (size_t)ntiles * kDescWords * sizeof(uint64_t), stream);
     if (rc) return rc;
     rc = workspace_next_epoch(ws, stream, &p.epoch);
     if (rc) return rc;
     p.state = ws_state(ws);
     p.ntiles = ntiles;
-    int64_t* splits = reinterpret_cast<int64_t*>(ws->payload);
-    p.splits = splits;
+    {
+        const char* dbg = getenv("SPB_DEBUG");
+        p.debug = dbg ? atoi(dbg) : 0;
+    }
+    p.desc = reinterpret_cast<uint64_t*>(ws->payload);
     auto kern = setop_kernel<V, VO, KIND, HAS_VAL, SEAM>;
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
@@ -537,9 +631,12 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
         SPB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kNT, smem));
         if (ctas_per_sm < 1) return SPB_ERR_UNSUPPORTED;
     }
-    const int64_t pwarps = ntiles + 1;
-    merge_partition_kernel<<<(unsigned)ceil_div(pwarps * 32, 256), 256, 0, stream>>>(p.a, p.na, p.b, p.nb, ntiles,
-                                                                                      splits);
+    PartitionParams pp{};
+    pp.a = p.a; pp.b = p.b; pp.na = p.na; pp.nb = p.nb; pp.a_val = p.a_val; pp.b_val = p.b_val;
+    pp.val_esize = Cfg<V, VO, KIND, HAS_VAL, SEAM>::kStageVals ? (int)sizeof(V) : 0;
+    pp.ntiles = ntiles;
+    pp.desc = reinterpret_cast<uint64_t*>(ws->payload);
+    merge_partition_kernel<<<(unsigned)ceil_div(ntiles * 32, 256), 256, 0, stream>>>(pp);
     SPB_LAUNCHED(1);
     int64_t grid = (int64_t)device_sm_count() * ctas_per_sm;          // persistent: every CTA is resident
     if (grid > ntiles) grid = ntiles;
