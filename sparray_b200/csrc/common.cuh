@@ -210,25 +210,26 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* state, in
     return total;
 }
 
-// Warp variant that inspects 8 predecessor tiles per lane (256 per round): for persistent
+// Warp variant that inspects W predecessor tiles per lane (32 W per round): for persistent
 // kernels whose look-back is deferred until the predecessors' counts are already published,
 // so one round of independent loads normally reaches the previous wave's prefix.
+template <int W = 8>
 __device__ __forceinline__ uint64_t lookback_exclusive_wide(const uint64_t* state, int64_t tile, uint32_t epoch) {
     const int lane = threadIdx.x & 31;
     uint64_t total = 0;
     int64_t base = tile - 1;
     while (base >= 0) {
-        uint64_t w[8];
+        uint64_t w[W];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int64_t t = base - (lane * 8 + j);
+        for (int j = 0; j < W; ++j) {
+            const int64_t t = base - (lane * W + j);
             w[j] = t >= 0 ? ld_state(state + t) : pack_state(kStPrefix, epoch, 0);
         }
         uint64_t part = 0;
         bool found = false;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int64_t t = base - (lane * 8 + j);
+        for (int j = 0; j < W; ++j) {
+            const int64_t t = base - (lane * W + j);
             while ((w[j] >> 62) == 0 || (uint32_t)((w[j] >> 48) & ((1u << kEpochBits) - 1)) != epoch) {
                 __nanosleep(20);
                 w[j] = ld_state(state + t);
@@ -243,7 +244,7 @@ __device__ __forceinline__ uint64_t lookback_exclusive_wide(const uint64_t* stat
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         total += v;
         if (has_prefix) break;
-        base -= 256;
+        base -= 32 * W;
     }
     return total;
 }

@@ -346,17 +346,37 @@ __device__ __forceinline__ void merge_walk(const Acc& A, const Acc& B, int ai, i
     m_emit = (KIND == KIND_UNION ? m_emit : m_eq) & live;
 }
 
+constexpr int kThreads = kNT + 32;      // 8 merger warps + 1 helper warp
+
+__device__ __forceinline__ void bar_mergers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised persistent kernel.
+//   helper warp (warp 8): keeps kNBuf tiles in flight (descriptor -> TMA copies, ragged edges,
+//     sentinels), and resolves the global output offset of every tile by decoupled look-back --
+//     both off the mergers' critical path;
+//   merger warps (0..7): wait for a staged tile, merge it, publish its output count, store the
+//     PREVIOUS tile's compacted outputs (their offset has been resolved meanwhile), stage this one.
+// Hand-shakes are mbarriers: full[slot] (helper+TMA -> mergers), empty[slot] (mergers -> helper),
+// agg[k] (count published -> helper), ready[k] (offset resolved -> mergers).
 template <typename V, typename VO, int KIND, bool HAS_VAL, bool SEAM>
-__global__ void __launch_bounds__(kNT, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMinCtas) setop_kernel(const SetopParams p) {
+__global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMinCtas) setop_kernel(const SetopParams p) {
     using C = Cfg<V, VO, KIND, HAS_VAL, SEAM>;
     using L = typename C::L;
     constexpr bool STAGE_VALS = C::kStageVals;
     constexpr int NBUF = C::kNBuf;
+    constexpr int VB = STAGE_VALS ? (int)sizeof(V) : 0;
     extern __shared__ __align__(128) char smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                 // [NBUF] one mbarrier per ring slot
-    Geom* geom = reinterpret_cast<Geom*>(smem + 32);                    // [NBUF] (40 bytes each)
-    int* warp_sums = reinterpret_cast<int*>(smem + 160);                // [8]
-    int64_t* base_s = reinterpret_cast<int64_t*>(smem + 192);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                 // [3]
+    uint64_t* empty = reinterpret_cast<uint64_t*>(smem + 24);           // [3]
+    uint64_t* agg = reinterpret_cast<uint64_t*>(smem + 48);             // [2]
+    uint64_t* ready = reinterpret_cast<uint64_t*>(smem + 64);           // [2]
+    Geom* geom = reinterpret_cast<Geom*>(smem + 80);                    // [3] (40 bytes each)
+    int* warp_sums = reinterpret_cast<int*>(smem + 200);                // [8]
+    int* tot_s = reinterpret_cast<int*>(smem + 232);                    // [2]
+    int64_t* base_s = reinterpret_cast<int64_t*>(smem + 240);           // [2]
     char* bufs = smem + L::kHeader;
     char* stg = bufs + NBUF * L::kBuf;
     // compacted outputs of the PREVIOUS tile wait here for their global offset
@@ -371,32 +391,88 @@ __global__ void __launch_bounds__(kNT, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMinCtas
     const int64_t stride = gridDim.x;
 
     if (tid == 0) {
-        for (int j = 0; j < NBUF; ++j) mbar_init(&full[j], 1);
+        for (int j = 0; j < NBUF; ++j) {
+            mbar_init(&full[j], 2);        // lane 0's expect_tx arrival + its "edges stored" arrival
+            mbar_init(&empty[j], 1);
+        }
+        for (int k = 0; k < 2; ++k) {
+            mbar_init(&agg[k], 1);
+            mbar_init(&ready[k], 1);
+        }
         fence_mbar_init();
     }
     __syncthreads();
 
-    // ---- prologue: fill the ring ------------------------------------------------------------------
-    EdgeReg er{0, 0, 0};
-    uint64_t dw_next = 0;                // warp 0: descriptor word of the tile that refills a slot next
-    constexpr int VB = STAGE_VALS ? (int)sizeof(V) : 0;
-    if (warp == 0) {
+    if (warp == kNT / 32) {
+        // =========================== helper warp ===========================================
+        EdgeReg er;
+        uint64_t dw = 0, dw_next = 0;
+        // begin: geometry, TMA copies and ragged-edge loads go in flight (descriptor word in `dw`)
+        auto stage_begin = [&](int slot_) {
+            prefetch_tile<VB>(dw, bufs + slot_ * L::kBuf, &full[slot_], &geom[slot_], er, lane);
+        };
+        // end: land the edge registers, write sentinels where a range touches the end of its array,
+        // then the second arrival on full[slot] tells the mergers that everything besides TMA is there
+        auto stage_end = [&](int slot_) {
+            char* buf = bufs + slot_ * L::kBuf;
+            edge_store(er);
+            const int64_t a0 = (int64_t)__shfl_sync(0xffffffffu, dw, 0), b0 = (int64_t)__shfl_sync(0xffffffffu, dw, 1);
+            const uint64_t nn = __shfl_sync(0xffffffffu, dw, 2), oo = __shfl_sync(0xffffffffu, dw, 3);
+            const int an = (int)(uint32_t)nn, bn = (int)(uint32_t)(nn >> 32);
+            int64_t* As64w = reinterpret_cast<int64_t*>(buf + (int)(uint32_t)oo);
+            int64_t* Bs64w = reinterpret_cast<int64_t*>(buf + (int)(uint32_t)(oo >> 32));
+            if (lane == 0 && a0 == 0) As64w[-1] = kKeyMin;
+            if (lane == 1 && a0 + an == p.na) As64w[an] = kKeyMax;
+            if (lane == 2 && b0 == 0) Bs64w[-1] = kKeyMin;
+            if (lane == 3 && b0 + bn == p.nb) Bs64w[bn] = kKeyMax;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[slot_]);
+        };
+        auto load_desc = [&](int64_t t) -> uint64_t {
+            return (t < p.ntiles && lane < kDescWords) ? __ldg(p.desc + t * kDescWords + lane) : 0;
+        };
         for (int j = 0; j < NBUF; ++j) {
             const int64_t t = blockIdx.x + j * stride;
             if (t < p.ntiles) {
-                const uint64_t dw = lane < kDescWords ? __ldg(p.desc + t * kDescWords + lane) : 0;
-                prefetch_tile<VB>(dw, bufs + j * L::kBuf, &full[j], &geom[j], er, lane);
-                edge_store(er);
+                dw = load_desc(t);
+                stage_begin(j);
+                stage_end(j);
             }
         }
-        er.dst = 0;
-        const int64_t t = blockIdx.x + NBUF * stride;
-        if (t < p.ntiles && lane < kDescWords) dw_next = __ldg(p.desc + t * kDescWords + lane);
+        dw_next = load_desc(blockIdx.x + NBUF * stride);
+        int slot = 0;
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
+            const int k = it & 1;
+            // (1) refill the ring slot this tile occupied, as soon as the mergers release it
+            const int64_t t2 = tile + NBUF * stride;
+            const bool refill = t2 < p.ntiles;
+            if (refill) {
+                mbar_wait(&empty[slot], (uint32_t)(it / NBUF) & 1u);
+                dw = dw_next;
+                stage_begin(slot);
+                dw_next = load_desc(t2 + stride);
+            }
+            // (2) global offset of this tile (its count is published at the same point of the mergers' loop)
+            mbar_wait(&agg[k], (uint32_t)(it >> 1) & 1u);
+            const int total = tot_s[k];
+            const uint64_t b = (tile > 0 && !(p.debug & 1)) ? lookback_exclusive_wide<16>(p.state, tile, p.epoch) : 0;
+            if (lane == 0) {
+                if (tile > 0) st_state(p.state + tile, pack_state(kStPrefix, p.epoch, b + (uint64_t)total));
+                if (tile == p.ntiles - 1) *p.out_count = (int64_t)b + total;
+                base_s[k] = (int64_t)b;
+                mbar_arrive(&ready[k]);
+            }
+            if (refill) stage_end(slot);
+            slot = slot + 1 == NBUF ? 0 : slot + 1;
+        }
+        return;
     }
-    uint32_t phase_bits = 0;
-    int64_t prev_tile = -1;      // tile whose outputs sit in the staging area
+
+    // =============================== merger warps ==========================================
     int prev_total = 0;
     int slot = 0;
+    int it = 0;
 
     auto store_prev = [&](int64_t base) {
         for (int i = tid; i < ((p.debug & 4) ? 0 : prev_total); i += kNT) {
@@ -413,36 +489,12 @@ __global__ void __launch_bounds__(kNT, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMinCtas
             }
         }
     };
-    // warp 0: global offset of the staged tile.  Its predecessors published their counts about one
-    // tile-iteration ago, so this normally does not wait.
-    auto lookback_prev = [&]() {
-        const uint64_t b = (prev_tile > 0 && !(p.debug & 1)) ? lookback_exclusive_wide(p.state, prev_tile, p.epoch) : 0;
-        if (lane == 0) {
-            if (prev_tile > 0) st_state(p.state + prev_tile, pack_state(kStPrefix, p.epoch, b + (uint64_t)prev_total));
-            if (prev_tile == p.ntiles - 1) *p.out_count = (int64_t)b + prev_total;
-            *base_s = (int64_t)b;
-        }
-    };
 
-    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += stride) {
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
         char* buf = bufs + slot * L::kBuf;
-        Geom* gs = &geom[slot];
-        if (warp == 0) {
-            edge_store(er);                                            // ragged edges of the tile prefetched last
-            er.dst = 0;
-            __syncwarp();                                              // lane 0 wrote the geometry when it prefetched
-            int64_t* As64w = reinterpret_cast<int64_t*>(buf + gs->offA);
-            int64_t* Bs64w = reinterpret_cast<int64_t*>(buf + gs->offB);
-            if (lane == 17 && gs->a0 == 0) As64w[-1] = kKeyMin;
-            if (lane == 18 && gs->a0 + gs->an == p.na) As64w[gs->an] = kKeyMax;
-            if (lane == 19 && gs->b0 == 0) Bs64w[-1] = kKeyMin;
-            if (lane == 20 && gs->b0 + gs->bn == p.nb) Bs64w[gs->bn] = kKeyMax;
-        }
-        mbar_wait(&full[slot], (phase_bits >> slot) & 1u);
-        phase_bits ^= 1u << slot;
-        __syncthreads();                                               // (A) tile, edges, sentinels, geometry, base
+        mbar_wait(&full[slot], (uint32_t)(it / NBUF) & 1u);
 
-        const Geom g = *gs;
+        const Geom g = geom[slot];
         const int an = g.an, bn = g.bn, items = an + bn;
         const int64_t* As64 = reinterpret_cast<const int64_t*>(buf + g.offA);
         const int64_t* Bs64 = reinterpret_cast<const int64_t*>(buf + g.offB);
@@ -460,7 +512,7 @@ __global__ void __launch_bounds__(kNT, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMinCtas
             int64_t* h = const_cast<int64_t*>(tid == 0 ? As64 + an : Bs64 + bn);
             if ((uint64_t)(*h - kbase) > 0xfffffffeull) *h = kbase + 0xffffffffll;
         }
-        __syncthreads();                                               // (B)
+        bar_mergers();                                                 // (B)
 
         // ---- per-thread merge-path split + branch-free walk ------------------------------------
         int diag = tid * kVT;
@@ -543,20 +595,7 @@ __global__ void __launch_bounds__(kNT, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMinCtas
             }
         }
         fence_proxy_async_smem();      // my generic reads of this slot happen-before the TMA that refills it
-        __syncthreads();                                               // (C) warp sums ready; the input tile is dead
-
-        // ---- refill this ring slot: kNBuf tiles ahead ------------------------------------------------
-        if (warp == 0) {
-            const int64_t t2 = tile + NBUF * stride;
-            if (t2 < p.ntiles) {
-                prefetch_tile<VB>(dw_next, buf, &full[slot], gs, er, lane);
-                const int64_t t3 = t2 + stride;
-                if (t3 < p.ntiles && lane < kDescWords) dw_next = __ldg(p.desc + t3 * kDescWords + lane);
-            }
-        }
-
-        // ... while warp 1 fetches the global offset of the tile staged one iteration ago
-        if (warp == 1 && prev_tile >= 0) lookback_prev();
+        bar_mergers();                                                 // (C) warp sums ready; the input tile is dead
 
         int wofs = 0, tile_total = 0;
 #pragma unroll
@@ -566,16 +605,21 @@ __global__ void __launch_bounds__(kNT, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMinCtas
             tile_total += s;
         }
         int off = wofs + incl - cnt;
-        // publish this tile's count right away: successors look back for it a whole iteration later
-        if (tid == 0)
+        const int k2 = it & 1;
+        if (tid == 0) {
+            mbar_arrive(&empty[slot]);                                 // the helper may refill this slot
+            // publish this tile's count right away: successors look back for it about one iteration later
             st_state(p.state + tile, pack_state(tile == 0 ? kStPrefix : kStAgg, p.epoch, (uint64_t)tile_total));
-
-        // ---- store the previous tile, then stage this one ---------------------------------------------
-        if (prev_tile >= 0) {
-            __syncthreads();                                           // (D) offset of the previous tile visible
-            store_prev(*base_s);
-            __syncthreads();                                           // (E) staging area drained
+            tot_s[k2] = tile_total;
+            mbar_arrive(&agg[k2]);                                     // the helper resolves this tile's offset
         }
+
+        // ---- store the previous tile (its offset was resolved while this one was merged) -----------
+        if (it > 0) {
+            mbar_wait(&ready[k2 ^ 1], (uint32_t)((it - 1) >> 1) & 1u);
+            store_prev(base_s[k2 ^ 1]);
+        }
+        bar_mergers();                                                 // (E) staging area drained
 #pragma unroll
         for (int k = 0; k < kVT; ++k) {
             if ((m_emit >> k) & 1u) {
@@ -589,15 +633,13 @@ __global__ void __launch_bounds__(kNT, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMinCtas
                 ++off;
             }
         }
-        prev_tile = tile;
         prev_total = tile_total;
         slot = slot + 1 == NBUF ? 0 : slot + 1;
     }
-    __syncthreads();
-    if (prev_tile >= 0) {
-        if (warp == 0) lookback_prev();
-        __syncthreads();
-        store_prev(*base_s);
+    if (it > 0) {
+        bar_mergers();                                                 // last tile staged
+        mbar_wait(&ready[(it - 1) & 1], (uint32_t)((it - 1) >> 1) & 1u);
+        store_prev(base_s[(it - 1) & 1]);
     }
 }
 
@@ -628,7 +670,7 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     if (!ctas_per_sm) {
         SPB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         SPB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        SPB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kNT, smem));
+        SPB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kThreads, smem));
         if (ctas_per_sm < 1) return SPB_ERR_UNSUPPORTED;
     }
     PartitionParams pp{};
@@ -640,7 +682,7 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     SPB_LAUNCHED(1);
     int64_t grid = (int64_t)device_sm_count() * ctas_per_sm;          // persistent: every CTA is resident
     if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, kNT, smem, stream>>>(p);
+    kern<<<(unsigned)grid, kThreads, smem, stream>>>(p);
     SPB_LAUNCHED(1);
     return (int)cudaGetLastError();
 }
