@@ -210,9 +210,9 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* state, in
     return total;
 }
 
-// Warp variant that inspects W predecessor tiles per lane (32 W per round): for persistent
-// kernels whose look-back is deferred until the predecessors' counts are already published,
-// so one round of independent loads normally reaches the previous wave's prefix.
+// Warp variant that inspects W predecessor tiles per lane (32 W per round, all loads in flight
+// at once).  It only ever waits for tiles NEARER than the nearest inclusive prefix it can see:
+// words farther back are ignored even if they are not published yet.
 template <int W = 8>
 __device__ __forceinline__ uint64_t lookback_exclusive_wide(const uint64_t* state, int64_t tile, uint32_t epoch) {
     const int lane = threadIdx.x & 31;
@@ -225,17 +225,40 @@ __device__ __forceinline__ uint64_t lookback_exclusive_wide(const uint64_t* stat
             const int64_t t = base - (lane * W + j);
             w[j] = t >= 0 ? ld_state(state + t) : pack_state(kStPrefix, epoch, 0);
         }
-        uint64_t part = 0;
-        bool found = false;
+        uint64_t part;
+        bool found;      // this lane reached a prefix with every nearer word of its own valid
+        bool clean;      // every word of this lane is valid
+        for (;;) {
+            part = 0;
+            found = false;
+            clean = true;
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
-            const int64_t t = base - (lane * W + j);
-            while ((w[j] >> 62) == 0 || (uint32_t)((w[j] >> 48) & ((1u << kEpochBits) - 1)) != epoch) {
-                __nanosleep(20);
-                w[j] = ld_state(state + t);
+            for (int j = 0; j < W; ++j) {
+                const bool valid = (w[j] >> 62) != 0 && (uint32_t)((w[j] >> 48) & ((1u << kEpochBits) - 1)) == epoch;
+                if (clean && !found) {
+                    if (!valid) clean = false;
+                    else {
+                        part += w[j] & kCountMask;
+                        found = (w[j] >> 62) == kStPrefix;
+                    }
+                }
             }
-            if (!found) part += w[j] & kCountMask;
-            found = found || (w[j] >> 62) == kStPrefix;
+            // nearest lane that reached a prefix; all nearer lanes must be fully valid
+            const unsigned fm = __ballot_sync(0xffffffffu, found);
+            const unsigned dirty = __ballot_sync(0xffffffffu, !clean && !found);
+            const int stop = fm ? (__ffs(fm) - 1) : 32;
+            const unsigned need = stop >= 32 ? 0xffffffffu : ((1u << stop) - 1u);
+            if ((dirty & need) == 0 && (fm || dirty == 0)) break;
+            // somebody nearer than the prefix is not published yet: poll those words again
+            if (!clean && !found && (lane < stop)) {
+                __nanosleep(40);
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+                    const int64_t t = base - (lane * W + j);
+                    const bool valid = (w[j] >> 62) != 0 && (uint32_t)((w[j] >> 48) & ((1u << kEpochBits) - 1)) == epoch;
+                    if (!valid && t >= 0) w[j] = ld_state(state + t);
+                }
+            }
         }
         const unsigned has_prefix = __ballot_sync(0xffffffffu, found);
         const int stop = has_prefix ? (__ffs(has_prefix) - 1) : 31;

@@ -135,16 +135,46 @@ struct PartitionParams {
     uint64_t* desc;          // [ntiles][kDescWords]
 };
 
-__global__ void __launch_bounds__(256) merge_partition_kernel(const PartitionParams p) {
-    const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+// 16 lanes per diagonal (two diagonals per warp): ~6 dependent rounds of 16 probe pairs each
+__global__ void __launch_bounds__(256) merge_splits_kernel(const PartitionParams p, int64_t* __restrict__ splits) {
+    const int64_t gthread = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t w = gthread >> 4;                    // diagonal index 0..ntiles
+    const int lane16 = threadIdx.x & 15;
+    const unsigned gmask = 0xffffu << (threadIdx.x & 16);
+    const bool active = w <= p.ntiles;
+    if (!active) w = p.ntiles;                   // keep the half-warp converged on a valid diagonal
+    const int64_t total = p.na + p.nb;
+    int64_t d = w * kTile;
+    if (d > total) d = total;
+    int64_t lo = d > p.nb ? d - p.nb : 0;
+    int64_t hi = d < p.na ? d : p.na;
+    while (lo < hi) {
+        const int64_t span = hi - lo;
+        const int64_t m = lo + ((span >> 4) * lane16) + (((span & 15) * lane16) >> 4);   // floor(span * lane / 16)
+        const bool take_a = __ldg(p.a + m) <= __ldg(p.b + (d - 1 - m));
+        const unsigned bal = (__ballot_sync(gmask, take_a) >> (threadIdx.x & 16)) & 0xffffu;
+        const int c = __popc(bal);
+        if (c == 0) {
+            hi = lo;
+            break;
+        }
+        const int src_base = threadIdx.x & 16;
+        const int64_t m_last_true = __shfl_sync(gmask, m, src_base + c - 1);
+        const int64_t m_first_false = __shfl_sync(gmask, m, src_base + (c < 16 ? c : 15));
+        lo = m_last_true + 1;
+        if (c < 16) hi = m_first_false;
+    }
+    if (active && lane16 == 0) splits[w] = lo;
+}
+
+__global__ void __launch_bounds__(256) merge_partition_kernel(const PartitionParams p, const int64_t* __restrict__ splits) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= p.ntiles) return;
     constexpr int kKeyReg = (kTile + 4) * 8 + 128 + kVT * 8;
     const int64_t total = p.na + p.nb;
     const int64_t d0 = t * kTile;
     const int64_t d1 = (d0 + kTile < total) ? d0 + kTile : total;
-    const int64_t a0 = merge_path_warp(p.a, p.na, p.b, p.nb, d0);
-    const int64_t a1 = merge_path_warp(p.a, p.na, p.b, p.nb, d1);
-    if ((threadIdx.x & 31) != 0) return;
+    const int64_t a0 = splits[t], a1 = splits[t + 1];
     const int64_t b0 = d0 - a0, b1 = d1 - a1;
     // indices [x0-1, x1] (one halo key either side), values [x0, x1) (+1 for B: partner of the last A)
     const int64_t ga_lo = a0 > 0 ? a0 - 1 : 0, ga_hi = a1 < p.na ? a1 + 1 : p.na;
@@ -226,9 +256,8 @@ struct Cfg {
     static constexpr int kCap = KIND == KIND_UNION ? kTile : kTile / 2;  // outputs per tile, at most
     static constexpr int kPayload = HAS_VAL ? kCap * (int)sizeof(VO)
                                             : (SEAM ? (KIND == KIND_UNION ? kCap : 2 * kCap * 8) : 0);
-    // tiles in flight per CTA: enough bytes on the wire per SM to cover HBM latency (Little's law)
-    static constexpr int kNBuf = (kStageVals && sizeof(V) == 8) ? 2 : 3;
-    static constexpr int kMinCtas = kStageVals ? 2 : 3;
+    static constexpr int kNBuf = 1;
+    static constexpr int kMinCtas = !kStageVals ? 6 : (sizeof(V) == 8 ? 3 : 4);   // what shared memory allows   // what shared memory allows
     using L = Layout<kStageVals ? (int)sizeof(V) : 0, kNBuf, kCap * 8, kPayload>;
 };
 
@@ -346,41 +375,25 @@ __device__ __forceinline__ void merge_walk(const Acc& A, const Acc& B, int ai, i
     m_emit = (KIND == KIND_UNION ? m_emit : m_eq) & live;
 }
 
-constexpr int kThreads = kNT + 32;      // 8 merger warps + 1 helper warp
+constexpr int kThreads = kNT;
 
-__device__ __forceinline__ void bar_mergers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// Warp-specialised persistent kernel.
-//   helper warp (warp 8): keeps kNBuf tiles in flight (descriptor -> TMA copies, ragged edges,
-//     sentinels), and resolves the global output offset of every tile by decoupled look-back --
-//     both off the mergers' critical path;
-//   merger warps (0..7): wait for a staged tile, merge it, publish its output count, store the
-//     PREVIOUS tile's compacted outputs (their offset has been resolved meanwhile), stage this one.
-// Hand-shakes are mbarriers: full[slot] (helper+TMA -> mergers), empty[slot] (mergers -> helper),
-// agg[k] (count published -> helper), ready[k] (offset resolved -> mergers).
+// One CTA = one tile (blockIdx order, so the decoupled look-back only ever waits on tiles that
+// started earlier).  Latency is hidden across the 3-4 CTAs resident per SM: while one waits for
+// its TMA copies, others merge or store.
 template <typename V, typename VO, int KIND, bool HAS_VAL, bool SEAM>
 __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMinCtas) setop_kernel(const SetopParams p) {
     using C = Cfg<V, VO, KIND, HAS_VAL, SEAM>;
     using L = typename C::L;
     constexpr bool STAGE_VALS = C::kStageVals;
-    constexpr int NBUF = C::kNBuf;
     constexpr int VB = STAGE_VALS ? (int)sizeof(V) : 0;
     extern __shared__ __align__(128) char smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                 // [3]
-    uint64_t* empty = reinterpret_cast<uint64_t*>(smem + 24);           // [3]
-    uint64_t* agg = reinterpret_cast<uint64_t*>(smem + 48);             // [2]
-    uint64_t* ready = reinterpret_cast<uint64_t*>(smem + 64);           // [2]
-    Geom* geom = reinterpret_cast<Geom*>(smem + 80);                    // [3] (40 bytes each)
-    int* warp_sums = reinterpret_cast<int*>(smem + 200);                // [8]
-    int* tot_s = reinterpret_cast<int*>(smem + 232);                    // [2]
-    int64_t* base_s = reinterpret_cast<int64_t*>(smem + 240);           // [2]
-    char* bufs = smem + L::kHeader;
-    char* stg = bufs + NBUF * L::kBuf;
-    // compacted outputs of the PREVIOUS tile wait here for their global offset
-    int64_t* skey = reinterpret_cast<int64_t*>(stg);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    Geom* geom = reinterpret_cast<Geom*>(smem + 16);                    // 40 bytes
+    int* warp_sums = reinterpret_cast<int*>(smem + 64);                 // [8]
+    int64_t* base_s = reinterpret_cast<int64_t*>(smem + 96);
+    char* buf = smem + L::kHeader;
+    char* stg = buf + L::kBuf;
+    int64_t* skey = reinterpret_cast<int64_t*>(stg);                    // compacted outputs
     VO* sval = reinterpret_cast<VO*>(stg + L::kStgKeys);
     uint8_t* slut = reinterpret_cast<uint8_t*>(stg + L::kStgKeys);
     int64_t* spa = reinterpret_cast<int64_t*>(stg + L::kStgKeys);
@@ -388,258 +401,167 @@ __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMi
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int64_t stride = gridDim.x;
+    const int64_t tile = blockIdx.x;
 
-    if (tid == 0) {
-        for (int j = 0; j < NBUF; ++j) {
-            mbar_init(&full[j], 2);        // lane 0's expect_tx arrival + its "edges stored" arrival
-            mbar_init(&empty[j], 1);
+    if (warp == 0) {
+        // ---- stage the tile: descriptor -> TMA bulk copies, ragged edges, sentinels -------------
+        const uint64_t dw = lane < kDescWords ? __ldg(p.desc + tile * kDescWords + lane) : 0;
+        if (lane == 0) {
+            mbar_init(full, 1);
+            fence_mbar_init();
         }
-        for (int k = 0; k < 2; ++k) {
-            mbar_init(&agg[k], 1);
-            mbar_init(&ready[k], 1);
-        }
-        fence_mbar_init();
-    }
-    __syncthreads();
-
-    if (warp == kNT / 32) {
-        // =========================== helper warp ===========================================
+        __syncwarp();
         EdgeReg er;
-        uint64_t dw = 0, dw_next = 0;
-        // begin: geometry, TMA copies and ragged-edge loads go in flight (descriptor word in `dw`)
-        auto stage_begin = [&](int slot_) {
-            prefetch_tile<VB>(dw, bufs + slot_ * L::kBuf, &full[slot_], &geom[slot_], er, lane);
-        };
-        // end: land the edge registers, write sentinels where a range touches the end of its array,
-        // then the second arrival on full[slot] tells the mergers that everything besides TMA is there
-        auto stage_end = [&](int slot_) {
-            char* buf = bufs + slot_ * L::kBuf;
-            edge_store(er);
-            const int64_t a0 = (int64_t)__shfl_sync(0xffffffffu, dw, 0), b0 = (int64_t)__shfl_sync(0xffffffffu, dw, 1);
-            const uint64_t nn = __shfl_sync(0xffffffffu, dw, 2), oo = __shfl_sync(0xffffffffu, dw, 3);
-            const int an = (int)(uint32_t)nn, bn = (int)(uint32_t)(nn >> 32);
-            int64_t* As64w = reinterpret_cast<int64_t*>(buf + (int)(uint32_t)oo);
-            int64_t* Bs64w = reinterpret_cast<int64_t*>(buf + (int)(uint32_t)(oo >> 32));
-            if (lane == 0 && a0 == 0) As64w[-1] = kKeyMin;
-            if (lane == 1 && a0 + an == p.na) As64w[an] = kKeyMax;
-            if (lane == 2 && b0 == 0) Bs64w[-1] = kKeyMin;
-            if (lane == 3 && b0 + bn == p.nb) Bs64w[bn] = kKeyMax;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[slot_]);
-        };
-        auto load_desc = [&](int64_t t) -> uint64_t {
-            return (t < p.ntiles && lane < kDescWords) ? __ldg(p.desc + t * kDescWords + lane) : 0;
-        };
-        for (int j = 0; j < NBUF; ++j) {
-            const int64_t t = blockIdx.x + j * stride;
-            if (t < p.ntiles) {
-                dw = load_desc(t);
-                stage_begin(j);
-                stage_end(j);
-            }
-        }
-        dw_next = load_desc(blockIdx.x + NBUF * stride);
-        int slot = 0;
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
-            const int k = it & 1;
-            // (1) refill the ring slot this tile occupied, as soon as the mergers release it
-            const int64_t t2 = tile + NBUF * stride;
-            const bool refill = t2 < p.ntiles;
-            if (refill) {
-                mbar_wait(&empty[slot], (uint32_t)(it / NBUF) & 1u);
-                dw = dw_next;
-                stage_begin(slot);
-                dw_next = load_desc(t2 + stride);
-            }
-            // (2) global offset of this tile (its count is published at the same point of the mergers' loop)
-            mbar_wait(&agg[k], (uint32_t)(it >> 1) & 1u);
-            const int total = tot_s[k];
-            const uint64_t b = (tile > 0 && !(p.debug & 1)) ? lookback_exclusive_wide<16>(p.state, tile, p.epoch) : 0;
-            if (lane == 0) {
-                if (tile > 0) st_state(p.state + tile, pack_state(kStPrefix, p.epoch, b + (uint64_t)total));
-                if (tile == p.ntiles - 1) *p.out_count = (int64_t)b + total;
-                base_s[k] = (int64_t)b;
-                mbar_arrive(&ready[k]);
-            }
-            if (refill) stage_end(slot);
-            slot = slot + 1 == NBUF ? 0 : slot + 1;
-        }
-        return;
+        prefetch_tile<VB>(dw, buf, full, geom, er, lane);
+        edge_store(er);
+        const int64_t a0 = (int64_t)__shfl_sync(0xffffffffu, dw, 0), b0 = (int64_t)__shfl_sync(0xffffffffu, dw, 1);
+        const uint64_t nn = __shfl_sync(0xffffffffu, dw, 2), oo = __shfl_sync(0xffffffffu, dw, 3);
+        const int an_ = (int)(uint32_t)nn, bn_ = (int)(uint32_t)(nn >> 32);
+        int64_t* As64w = reinterpret_cast<int64_t*>(buf + (int)(uint32_t)oo);
+        int64_t* Bs64w = reinterpret_cast<int64_t*>(buf + (int)(uint32_t)(oo >> 32));
+        if (lane == 0 && a0 == 0) As64w[-1] = kKeyMin;
+        if (lane == 1 && a0 + an_ == p.na) As64w[an_] = kKeyMax;
+        if (lane == 2 && b0 == 0) Bs64w[-1] = kKeyMin;
+        if (lane == 3 && b0 + bn_ == p.nb) Bs64w[bn_] = kKeyMax;
+    }
+    __syncthreads();                                                   // (A) barrier initialised, geometry / edges visible
+    mbar_wait(full, 0);
+
+    const Geom g = *geom;
+    const int an = g.an, bn = g.bn, items = an + bn;
+    const int64_t* As64 = reinterpret_cast<const int64_t*>(buf + g.offA);
+    const int64_t* Bs64 = reinterpret_cast<const int64_t*>(buf + g.offB);
+
+    // ---- 32-bit tile-local keys when the span allows it ---------------------------------------
+    const int64_t first_a = an ? As64[0] : kKeyMax, first_b = bn ? Bs64[0] : kKeyMax;
+    const int64_t last_a = an ? As64[an - 1] : kKeyMin, last_b = bn ? Bs64[bn - 1] : kKeyMin;
+    const int64_t kbase = first_a < first_b ? first_a : first_b;
+    const int64_t kmax = last_a > last_b ? last_a : last_b;
+    const bool narrow = (uint64_t)(kmax - kbase) < 0xfffffffeull;
+    const bool front_dup = bn > 0 && As64[-1] == Bs64[0];              // A's last key of the previous tile pairs B's first
+    if (narrow && tid < 2) {
+        // the halo / sentinel key behind each range may lie beyond the 32-bit window: clamp it to the
+        // largest offset, which no key of the tile can reach
+        int64_t* h = const_cast<int64_t*>(tid == 0 ? As64 + an : Bs64 + bn);
+        if ((uint64_t)(*h - kbase) > 0xfffffffeull) *h = kbase + 0xffffffffll;
+    }
+    __syncthreads();                                                   // (B)
+
+    // ---- per-thread merge-path split + branch-free walk ------------------------------------
+    int diag = tid * kVT;
+    if (diag > items) diag = items;
+    const int steps = (items - diag) < kVT ? (items - diag) : kVT;
+    int ai0, bi0;
+    unsigned m_ta, m_eq, m_emit;
+    if (p.debug & 2) {
+        ai0 = diag / 2; bi0 = diag - ai0; m_ta = 0x55; m_eq = 0; m_emit = KIND == KIND_UNION ? 0xff : 0;
+    } else if (narrow) {
+        const NarrowKeys A{reinterpret_cast<const uint32_t*>(As64), (uint32_t)kbase};
+        const NarrowKeys B{reinterpret_cast<const uint32_t*>(Bs64), (uint32_t)kbase};
+        ai0 = merge_path_smem(A, an, B, bn, diag);
+        bi0 = diag - ai0;
+        const bool prev_eq = ai0 > 0 ? (A(ai0 - 1) == B(bi0)) : (bi0 == 0 && front_dup);
+        merge_walk<NarrowKeys, KIND>(A, B, ai0, bi0, steps, prev_eq, m_ta, m_eq, m_emit);
+    } else {
+        const WideKeys A{As64}, B{Bs64};
+        ai0 = merge_path_smem(A, an, B, bn, diag);
+        bi0 = diag - ai0;
+        const bool prev_eq = ai0 > 0 ? (A(ai0 - 1) == B(bi0)) : (bi0 == 0 && front_dup);
+        merge_walk<WideKeys, KIND>(A, B, ai0, bi0, steps, prev_eq, m_ta, m_eq, m_emit);
     }
 
-    // =============================== merger warps ==========================================
-    int prev_total = 0;
-    int slot = 0;
-    int it = 0;
+    // ---- block exclusive scan of the output counts -------------------------------------------
+    const int cnt = __popc(m_emit);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();                                                   // (C)
+    int wofs = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kNT / 32; ++w) {
+        const int s = warp_sums[w];
+        if (w < warp) wofs += s;
+        tile_total += s;
+    }
+    int off = wofs + incl - cnt;
 
-    auto store_prev = [&](int64_t base) {
-        for (int i = tid; i < ((p.debug & 4) ? 0 : prev_total); i += kNT) {
-            if constexpr (SEAM && KIND == KIND_INTERSECT) {
-                p.out_idx[base + i] = skey[i];
-                if (p.a_pos) p.a_pos[base + i] = spa[i];
-                if (p.b_pos) p.b_pos[base + i] = spb_[i];
-            } else {
-                p.out_idx[base + i] = skey[i];
-                if constexpr (HAS_VAL) reinterpret_cast<VO*>(p.out_val)[base + i] = sval[i];
-                if constexpr (SEAM && KIND == KIND_UNION) {
-                    if (p.lut) p.lut[base + i] = slut[i];
-                }
-            }
-        }
-    };
-
-    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
-        char* buf = bufs + slot * L::kBuf;
-        mbar_wait(&full[slot], (uint32_t)(it / NBUF) & 1u);
-
-        const Geom g = geom[slot];
-        const int an = g.an, bn = g.bn, items = an + bn;
-        const int64_t* As64 = reinterpret_cast<const int64_t*>(buf + g.offA);
-        const int64_t* Bs64 = reinterpret_cast<const int64_t*>(buf + g.offB);
-
-        // ---- 32-bit tile-local keys when the span allows it ---------------------------------------
-        const int64_t first_a = an ? As64[0] : kKeyMax, first_b = bn ? Bs64[0] : kKeyMax;
-        const int64_t last_a = an ? As64[an - 1] : kKeyMin, last_b = bn ? Bs64[bn - 1] : kKeyMin;
-        const int64_t kbase = first_a < first_b ? first_a : first_b;
-        const int64_t kmax = last_a > last_b ? last_a : last_b;
-        const bool narrow = (uint64_t)(kmax - kbase) < 0xfffffffeull;
-        const bool front_dup = bn > 0 && As64[-1] == Bs64[0];          // A's last key of the previous tile pairs B's first
-        if (narrow && tid < 2) {
-            // the halo / sentinel key behind each range may lie beyond the 32-bit window: clamp it to the
-            // largest offset, which no key of the tile can reach
-            int64_t* h = const_cast<int64_t*>(tid == 0 ? As64 + an : Bs64 + bn);
-            if ((uint64_t)(*h - kbase) > 0xfffffffeull) *h = kbase + 0xffffffffll;
-        }
-        bar_mergers();                                                 // (B)
-
-        // ---- per-thread merge-path split + branch-free walk ------------------------------------
-        int diag = tid * kVT;
-        if (diag > items) diag = items;
-        const int steps = (items - diag) < kVT ? (items - diag) : kVT;
-        int ai0, bi0;
-        unsigned m_ta, m_eq, m_emit;
-        if (p.debug & 2) {
-            ai0 = diag / 2; bi0 = diag - ai0; m_ta = 0x55; m_eq = 0; m_emit = KIND == KIND_UNION ? 0xff : 0;
-        } else if (narrow) {
-            const NarrowKeys A{reinterpret_cast<const uint32_t*>(As64), (uint32_t)kbase};
-            const NarrowKeys B{reinterpret_cast<const uint32_t*>(Bs64), (uint32_t)kbase};
-            ai0 = merge_path_smem(A, an, B, bn, diag);
-            bi0 = diag - ai0;
-            const bool prev_eq = ai0 > 0 ? (A(ai0 - 1) == B(bi0)) : (bi0 == 0 && front_dup);
-            merge_walk<NarrowKeys, KIND>(A, B, ai0, bi0, steps, prev_eq, m_ta, m_eq, m_emit);
+    // ---- publish the count, then look back (warp 0) while the other warps materialise -----------
+    if (warp == 0) {
+        uint64_t b = 0;
+        if (tile == 0) {
+            if (lane == 0) st_state(p.state, pack_state(kStPrefix, p.epoch, (uint64_t)tile_total));
         } else {
-            const WideKeys A{As64}, B{Bs64};
-            ai0 = merge_path_smem(A, an, B, bn, diag);
-            bi0 = diag - ai0;
-            const bool prev_eq = ai0 > 0 ? (A(ai0 - 1) == B(bi0)) : (bi0 == 0 && front_dup);
-            merge_walk<WideKeys, KIND>(A, B, ai0, bi0, steps, prev_eq, m_ta, m_eq, m_emit);
+            if (lane == 0) st_state(p.state + tile, pack_state(kStAgg, p.epoch, (uint64_t)tile_total));
+            if (!(p.debug & 1)) b = lookback_exclusive(p.state, tile, p.epoch);
+            if (lane == 0) st_state(p.state + tile, pack_state(kStPrefix, p.epoch, b + (uint64_t)tile_total));
         }
+        if (lane == 0) {
+            *base_s = (int64_t)b;
+            if (tile == (int64_t)gridDim.x - 1) *p.out_count = (int64_t)b + tile_total;
+        }
+    }
 
-        // ---- block exclusive scan of the output counts -------------------------------------------
-        const int cnt = __popc(m_emit);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) warp_sums[warp] = incl;
-
-        // ---- materialise the emitted items in registers -------------------------------------------
-        int64_t okey[kVT];
-        VO oval[kVT];
-        int64_t opa[SEAM && KIND == KIND_INTERSECT ? kVT : 1];
-        int64_t opb[SEAM && KIND == KIND_INTERSECT ? kVT : 1];
-        uint8_t olut[SEAM && KIND == KIND_UNION ? kVT : 1];
-        if (KIND == KIND_UNION || m_emit != 0) {
-            const V* Av = STAGE_VALS ? reinterpret_cast<const V*>(buf + g.offAv) : nullptr;
-            const V* Bv = STAGE_VALS ? reinterpret_cast<const V*>(buf + g.offBv) : nullptr;
-            int ai = ai0, bi = bi0;
-#pragma unroll
-            for (int k = 0; k < kVT; ++k) {
-                const bool ta = (m_ta >> k) & 1u, eq = ta && ((m_eq >> k) & 1u), e = (m_emit >> k) & 1u;
-                if (e) {
-                    okey[k] = ta ? As64[ai] : Bs64[bi];
-                    if constexpr (HAS_VAL) {
-                        V x, y;
-                        if constexpr (STAGE_VALS) {
-                            x = ta ? Av[ai] : V(0);
-                            y = (!ta || eq) ? Bv[bi] : V(0);
-                            if (p.negate_b && (!ta || eq)) y = (V)(-y);
-                        } else {   // intersection: only matched values are ever read
-                            x = __ldg(reinterpret_cast<const V*>(p.a_val) + g.a0 + ai);
-                            y = __ldg(reinterpret_cast<const V*>(p.b_val) + g.b0 + bi);
-                            if (p.negate_b) y = (V)(-y);
-                        }
-                        oval[k] = value_op<V, VO>(p.op, x, y);
-                    }
-                    if constexpr (SEAM && KIND == KIND_UNION) olut[k] = ta ? (eq ? 2 : 0) : 1;
-                    if constexpr (SEAM && KIND == KIND_INTERSECT) {
-                        opa[k] = g.a0 + ai;
-                        opb[k] = g.b0 + bi;
-                    }
-                }
-                if constexpr (SEAM && KIND == KIND_UNION) {
-                    if (k < steps) {
-                        if (ta) {
-                            if (p.a_only) p.a_only[g.a0 + ai] = eq ? 0 : 1;
-                        } else {
-                            if (p.b_only) p.b_only[g.b0 + bi] = e ? 1 : 0;
-                        }
-                    }
-                }
-                ai += ta ? 1 : 0;
-                bi += ta ? 0 : ((k < steps) ? 1 : 0);
-            }
-        }
-        fence_proxy_async_smem();      // my generic reads of this slot happen-before the TMA that refills it
-        bar_mergers();                                                 // (C) warp sums ready; the input tile is dead
-
-        int wofs = 0, tile_total = 0;
-#pragma unroll
-        for (int w = 0; w < kNT / 32; ++w) {
-            const int s = warp_sums[w];
-            if (w < warp) wofs += s;
-            tile_total += s;
-        }
-        int off = wofs + incl - cnt;
-        const int k2 = it & 1;
-        if (tid == 0) {
-            mbar_arrive(&empty[slot]);                                 // the helper may refill this slot
-            // publish this tile's count right away: successors look back for it about one iteration later
-            st_state(p.state + tile, pack_state(tile == 0 ? kStPrefix : kStAgg, p.epoch, (uint64_t)tile_total));
-            tot_s[k2] = tile_total;
-            mbar_arrive(&agg[k2]);                                     // the helper resolves this tile's offset
-        }
-
-        // ---- store the previous tile (its offset was resolved while this one was merged) -----------
-        if (it > 0) {
-            mbar_wait(&ready[k2 ^ 1], (uint32_t)((it - 1) >> 1) & 1u);
-            store_prev(base_s[k2 ^ 1]);
-        }
-        bar_mergers();                                                 // (E) staging area drained
+    // ---- materialise the emitted items straight into the staging area --------------------------
+    if (KIND == KIND_UNION || m_emit != 0) {
+        const V* Av = STAGE_VALS ? reinterpret_cast<const V*>(buf + g.offAv) : nullptr;
+        const V* Bv = STAGE_VALS ? reinterpret_cast<const V*>(buf + g.offBv) : nullptr;
+        int ai = ai0, bi = bi0;
 #pragma unroll
         for (int k = 0; k < kVT; ++k) {
-            if ((m_emit >> k) & 1u) {
-                skey[off] = okey[k];
-                if constexpr (HAS_VAL) sval[off] = oval[k];
-                if constexpr (SEAM && KIND == KIND_UNION) slut[off] = olut[k];
+            const bool ta = (m_ta >> k) & 1u, eq = ta && ((m_eq >> k) & 1u), e = (m_emit >> k) & 1u;
+            if (e) {
+                skey[off] = ta ? As64[ai] : Bs64[bi];
+                if constexpr (HAS_VAL) {
+                    V x, y;
+                    if constexpr (STAGE_VALS) {
+                        x = ta ? Av[ai] : V(0);
+                        y = (!ta || eq) ? Bv[bi] : V(0);
+                        if (p.negate_b && (!ta || eq)) y = (V)(-y);
+                    } else {   // intersection: only matched values are ever read
+                        x = __ldg(reinterpret_cast<const V*>(p.a_val) + g.a0 + ai);
+                        y = __ldg(reinterpret_cast<const V*>(p.b_val) + g.b0 + bi);
+                        if (p.negate_b) y = (V)(-y);
+                    }
+                    sval[off] = value_op<V, VO>(p.op, x, y);
+                }
+                if constexpr (SEAM && KIND == KIND_UNION) slut[off] = ta ? (eq ? 2 : 0) : 1;
                 if constexpr (SEAM && KIND == KIND_INTERSECT) {
-                    spa[off] = opa[k];
-                    spb_[off] = opb[k];
+                    spa[off] = g.a0 + ai;
+                    spb_[off] = g.b0 + bi;
                 }
                 ++off;
             }
+            if constexpr (SEAM && KIND == KIND_UNION) {
+                if (k < steps) {
+                    if (ta) {
+                        if (p.a_only) p.a_only[g.a0 + ai] = eq ? 0 : 1;
+                    } else {
+                        if (p.b_only) p.b_only[g.b0 + bi] = e ? 1 : 0;
+                    }
+                }
+            }
+            ai += ta ? 1 : 0;
+            bi += ta ? 0 : ((k < steps) ? 1 : 0);
         }
-        prev_total = tile_total;
-        slot = slot + 1 == NBUF ? 0 : slot + 1;
     }
-    if (it > 0) {
-        bar_mergers();                                                 // last tile staged
-        mbar_wait(&ready[(it - 1) & 1], (uint32_t)((it - 1) >> 1) & 1u);
-        store_prev(base_s[(it - 1) & 1]);
+    __syncthreads();                                                   // (D) staging + offset visible
+    const int64_t base = *base_s;
+    for (int i = tid; i < ((p.debug & 4) ? 0 : tile_total); i += kNT) {
+        if constexpr (SEAM && KIND == KIND_INTERSECT) {
+            p.out_idx[base + i] = skey[i];
+            if (p.a_pos) p.a_pos[base + i] = spa[i];
+            if (p.b_pos) p.b_pos[base + i] = spb_[i];
+        } else {
+            p.out_idx[base + i] = skey[i];
+            if constexpr (HAS_VAL) reinterpret_cast<VO*>(p.out_val)[base + i] = sval[i];
+            if constexpr (SEAM && KIND == KIND_UNION) {
+                if (p.lut) p.lut[base + i] = slut[i];
+            }
+        }
     }
 }
 
@@ -654,7 +576,7 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
     int rc = workspace_reserve(ws, (size_t)ntiles * sizeof(uint64_t), stream);
     if (rc) return rc;
-    rc = workspace_reserve_payload(ws, (size_t)ntiles * kDescWords * sizeof(uint64_t), stream);
+    rc = workspace_reserve_payload(ws, (size_t)ntiles * kDescWords * sizeof(uint64_t) + (size_t)(ntiles + 1) * 8, stream);
     if (rc) return rc;
     rc = workspace_next_epoch(ws, stream, &p.epoch);
     if (rc) return rc;
@@ -678,11 +600,12 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     pp.val_esize = Cfg<V, VO, KIND, HAS_VAL, SEAM>::kStageVals ? (int)sizeof(V) : 0;
     pp.ntiles = ntiles;
     pp.desc = reinterpret_cast<uint64_t*>(ws->payload);
-    merge_partition_kernel<<<(unsigned)ceil_div(ntiles * 32, 256), 256, 0, stream>>>(pp);
+    int64_t* splits = reinterpret_cast<int64_t*>(pp.desc + ntiles * kDescWords);
+    merge_splits_kernel<<<(unsigned)ceil_div((ntiles + 1) * 16, 256), 256, 0, stream>>>(pp, splits);
     SPB_LAUNCHED(1);
-    int64_t grid = (int64_t)device_sm_count() * ctas_per_sm;          // persistent: every CTA is resident
-    if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, kThreads, smem, stream>>>(p);
+    merge_partition_kernel<<<(unsigned)ceil_div(ntiles, 256), 256, 0, stream>>>(pp, splits);
+    SPB_LAUNCHED(1);
+    kern<<<(unsigned)ntiles, kThreads, smem, stream>>>(p);
     SPB_LAUNCHED(1);
     return (int)cudaGetLastError();
 }
