@@ -1,0 +1,328 @@
+"""Range-sharded FlatSparray across the GPUs of one NVSwitch box (one process per GPU,
+``torch.distributed``; NCCL on GPUs, gloo in the CPU tests).
+
+The reference has no distributed code at all: this layer is new
+design.  An array is split by contiguous FLAT-INDEX RANGES -- rank r owns the stored
+elements with ``splitters[r] <= flat index < splitters[r + 1]`` -- so every shard is itself
+a canonical (sorted, duplicate-free) ``(indices, data)`` pair and the single-GPU kernels
+run on it unchanged.
+
+  * co-partitioned binops (same splitters on both operands): purely local, NO collective;
+  * misaligned operands: ``repartition`` = allgather of the send counts + ONE variable-size
+    all-to-all of (index, value) segments.  Each shard is sorted, so the segment for every
+    destination is a contiguous slice (found by a batched binary search of the splitters),
+    and because the source partition is itself a range partition, concatenating the
+    received segments in source-rank order is already globally sorted: no merge, no sort;
+  * axis sums: local segmented reduce; only output keys on a shard border can collide, so
+    the borders are fixed by an allgather of one (key, value) pair per rank -- or, when the
+    reduced axis is not the last one, an all-to-all of the partial sums by output-key range
+    followed by a local merge-reduce;
+  * transpose: re-key locally, all-to-all by new-key splitters, local sort;
+  * SpMV: rows follow flat ranges (row-major), x is replicated, y partials are all-reduced.
+
+The kernels are reached through a small ``ops`` object so the orchestration (splitter
+choice, counts exchange, all-to-all plumbing, border fix-up) can be exercised with
+world_size 2 on CPU under gloo; the shipped default is ``CudaOps`` and there is no CPU
+fallback -- the tests inject their own checker ops.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class CudaOps:
+    """Local kernels on this rank's GPU (the product path)."""
+
+    def __init__(self):
+        from . import _kernels
+        self.k = _kernels
+
+    def lower_bound(self, sorted_idx, query):
+        return self.k.lower_bound(sorted_idx, query, want_found=False)[0]
+
+    def binop(self, kind, op, a_idx, a_val, b_idx, b_val):
+        from . import _dtypes as dt
+        if a_val.dtype != b_val.dtype:
+            common = dt.promote(a_val.dtype, b_val.dtype)
+            a_val = self.k.cast(a_val, common) if a_val.dtype != common else a_val
+            b_val = self.k.cast(b_val, common) if b_val.dtype != common else b_val
+        return self.k.setop_binop(kind, op, a_idx, a_val, b_idx, b_val)
+
+    def reduce_by_key(self, keys, vals, divisor=1):
+        return self.k.reduce_by_key(keys, vals, divisor)
+
+    def rekey_sort(self, idx, val, in_s, out_s, div, bits):
+        return self.k.rekey_sort(idx, val, in_s, out_s, div, bits)
+
+    def spmv(self, idx, val, ncols, nrows, x):
+        return self.k.spmv(idx, val, ncols, nrows, x, val.dtype)
+
+    def device(self):
+        return torch.device("cuda", torch.cuda.current_device())
+
+
+def _size(shape):
+    return int(np.prod([int(s) for s in shape], dtype=object))
+
+
+def even_splitters(shape, world):
+    """world + 1 flat-index boundaries of (almost) equal width, aligned to whole rows of the
+    leading axis when that is possible (so that last-axis reductions and SpMV never straddle)."""
+    size = _size(shape)
+    row = size // int(shape[0]) if shape and shape[0] else 1
+    nrows = size // row if row else 0
+    if nrows >= world:
+        cuts = [(nrows * r // world) * row for r in range(world)]
+    else:
+        cuts = [size * r // world for r in range(world)]
+    return cuts + [size]
+
+
+def sampled_splitters(local_idx, shape, group=None, ops=None, samples_per_rank=256):
+    """Splitters that balance nnz: every rank contributes evenly spaced samples of its sorted
+    indices, the samples are all-gathered (a few KB), and the r/world quantiles become the
+    boundaries."""
+    world = dist.get_world_size(group)
+    n = local_idx.numel()
+    take = min(samples_per_rank, n)
+    if take:
+        pos = torch.linspace(0, n - 1, take, device=local_idx.device).long()
+        sample = local_idx[pos]
+    else:
+        sample = local_idx[:0]
+    padded = torch.full((samples_per_rank,), -1, dtype=torch.int64, device=local_idx.device)
+    padded[:take] = sample
+    gathered = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(gathered, padded, group=group)
+    allv = torch.cat(gathered)
+    allv = allv[allv >= 0].cpu().numpy()
+    allv.sort()
+    size = _size(shape)
+    if len(allv) == 0:
+        return even_splitters(shape, world)
+    cuts = [0] + [int(allv[len(allv) * r // world]) for r in range(1, world)] + [size]
+    for r in range(1, world + 1):          # keep them monotone
+        cuts[r] = max(cuts[r], cuts[r - 1])
+    return cuts
+
+
+class ShardedFlatSparray:
+    """This rank's shard of a range-partitioned FlatSparray."""
+
+    def __init__(self, indices, data, shape, splitters, group=None, ops=None):
+        self.indices, self.data = indices, data
+        self.shape = tuple(int(s) for s in shape)
+        self.splitters = [int(s) for s in splitters]
+        self.group = group
+        self.ops = ops if ops is not None else CudaOps()
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        assert len(self.splitters) == self.world + 1
+
+    @property
+    def nnz_local(self):
+        return int(self.indices.numel())
+
+    def nnz(self):
+        t = torch.tensor([self.nnz_local], dtype=torch.int64, device=self.indices.device)
+        dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
+    def _like(self, indices, data, shape=None, splitters=None):
+        return ShardedFlatSparray(indices, data, shape or self.shape, splitters or self.splitters,
+                                  self.group, self.ops)
+
+    # ---- co-partitioned / repartitioned binops -------------------------------------------------------
+    def _binop(self, other, kind, op):
+        assert self.shape == other.shape
+        if other.splitters != self.splitters:
+            other = other.repartition(self.splitters)       # the only communication of a binop
+        idx, val = self.ops.binop(kind, op, self.indices, self.data, other.indices, other.data)
+        return self._like(idx, val)
+
+    def __add__(self, other):
+        return self._binop(other, "union", "add")
+
+    def __sub__(self, other):
+        return self._binop(other, "union", "sub")
+
+    def __mul__(self, other):
+        return self._binop(other, "intersect", "mul")
+
+    def minimum(self, other):
+        return self._binop(other, "union", "minimum")
+
+    def maximum(self, other):
+        return self._binop(other, "union", "maximum")
+
+    # ---- repartition: counts allgather + one variable-size all-to-all --------------------------------
+    def repartition(self, new_splitters):
+        new_splitters = [int(s) for s in new_splitters]
+        dev = self.indices.device
+        # destination d receives my elements in [new[d], new[d+1]): a contiguous slice of my sorted shard
+        bounds = torch.tensor(new_splitters, dtype=torch.int64, device=dev)
+        cut = self.ops.lower_bound(self.indices, bounds).cpu().tolist()
+        send_counts = [cut[d + 1] - cut[d] for d in range(self.world)]
+        counts = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+        all_counts = [torch.empty_like(counts) for _ in range(self.world)]
+        dist.all_gather(all_counts, counts, group=self.group)
+        recv_counts = [int(all_counts[s][self.rank].item()) for s in range(self.world)]
+        lo = cut[0]
+        send_idx = self.indices[lo:cut[-1]].contiguous()
+        send_val = self.data[lo:cut[-1]].contiguous()
+        recv_idx = torch.empty(sum(recv_counts), dtype=torch.int64, device=dev)
+        recv_val = torch.empty(sum(recv_counts), dtype=self.data.dtype, device=dev)
+        dist.all_to_all_single(recv_idx, send_idx, recv_counts, send_counts, group=self.group)
+        dist.all_to_all_single(recv_val, send_val, recv_counts, send_counts, group=self.group)
+        # sources are range-ordered, so the concatenation in source order is globally sorted
+        return self._like(recv_idx, recv_val, splitters=new_splitters)
+
+    # ---- reductions -------------------------------------------------------------------------------------
+    def sum(self, axis):
+        """sum over one axis -> ShardedFlatSparray with float64 data (flat.py:607-626)."""
+        from . import _plan
+        axis = int(axis) % len(self.shape)
+        new_shape = self.shape[:axis] + self.shape[axis + 1:]
+        plan = _plan.axis_sum_plan(self.shape, axis)
+        dev = self.indices.device
+        if plan[0] == "last":
+            div = plan[1]
+            keys, sums = self.ops.reduce_by_key(self.indices, self.data, div)
+            new_split = [s // div for s in self.splitters[:-1]] + [_size(new_shape)]
+            return self._fix_borders(keys, sums, new_shape, new_split)
+        # middle axis: local re-key + sort + reduce, then exchange partial sums by output-key range
+        _, in_s, out_s, bits = plan
+        keys, vals = self.ops.rekey_sort(self.indices, self.data, in_s, out_s, 1, bits)
+        keys, sums = self.ops.reduce_by_key(keys, vals, 1)
+        out_split = even_splitters(new_shape, self.world)
+        part = ShardedFlatSparray(keys, sums, new_shape, [0] * self.world + [_size(new_shape)], self.group, self.ops)
+        part.splitters = None                                 # not range-partitioned yet
+        got = _exchange_unsorted(part, out_split)
+        # every source contributed a sorted run: sort by key again (bits of the output key) and reduce
+        kbits = max(_size(new_shape) - 1, 1).bit_length()
+        k2, v2 = self.ops.rekey_sort(got[0], got[1], [], [], 1, kbits)
+        k3, s3 = self.ops.reduce_by_key(k2, v2, 1)
+        return ShardedFlatSparray(k3, s3, new_shape, out_split, self.group, self.ops)
+
+    def _fix_borders(self, keys, sums, new_shape, new_split):
+        """After a last-axis reduction only the FIRST output key of a rank can also be the last
+        key of an earlier rank (a shard boundary inside a row).  Everybody all-gathers
+        (first key, last key, count, first sum); the earliest rank of each chain keeps the key
+        and absorbs the partial sums, the others drop their first element."""
+        dev = keys.device
+        n = keys.numel()
+        meta = torch.tensor([int(keys[0]) if n else -1, int(keys[-1]) if n else -1, n], dtype=torch.int64, device=dev)
+        info = torch.zeros(1, dtype=torch.float64, device=dev)
+        if n:
+            info[0] = sums[0]
+        metas = [torch.empty_like(meta) for _ in range(self.world)]
+        infos = [torch.empty_like(info) for _ in range(self.world)]
+        dist.all_gather(metas, meta, group=self.group)
+        dist.all_gather(infos, info, group=self.group)
+        firsts = [int(m[0]) for m in metas]
+        lasts = [int(m[1]) for m in metas]
+        counts = [int(m[2]) for m in metas]
+        dup = [False] * self.world
+        owner = list(range(self.world))
+        prev = None
+        for r in range(self.world):
+            if counts[r] == 0:
+                continue
+            if prev is not None and lasts[prev] == firsts[r]:
+                dup[r] = True
+                owner[r] = owner[prev] if (counts[prev] == 1 and dup[prev]) else prev
+            prev = r
+        sums = sums.clone()
+        if dup[self.rank]:
+            keys, sums = keys[1:], sums[1:]
+        for r in range(self.rank + 1, self.world):
+            if dup[r] and owner[r] == self.rank:
+                sums[-1] += infos[r][0].to(sums.device)
+        return ShardedFlatSparray(keys, sums, new_shape, new_split, self.group, self.ops)
+
+    # ---- SpMV --------------------------------------------------------------------------------------------
+    def dot(self, x):
+        """a.dot(x) for a replicated dense vector x -> replicated dense y (float64 partials all-reduced)."""
+        ncols = self.shape[-1]
+        nrows = _size(self.shape) // ncols
+        y = self.ops.spmv(self.indices, self.data, ncols, nrows, x)
+        y = y.to(torch.float64)
+        dist.all_reduce(y, group=self.group)
+        return y.reshape(self.shape[:-1])
+
+    # ---- transpose ---------------------------------------------------------------------------------------
+    def transpose(self, *axes):
+        from . import _plan
+        ndim = len(self.shape)
+        axes = tuple(range(ndim - 1, -1, -1)) if not axes else tuple(int(a) for a in axes)
+        new_shape = tuple(self.shape[a] for a in axes)
+        in_s, out_s, _, _ = _plan.transpose_plan(self.shape, axes)
+        keys, vals = self.ops.rekey_sort(self.indices, self.data, in_s, out_s, 1, 0)     # re-key only
+        out_split = even_splitters(new_shape, self.world)
+        part = ShardedFlatSparray(keys, vals, new_shape, [0] * (self.world + 1), self.group, self.ops)
+        got = _exchange_unsorted(part, out_split)
+        kbits = max(_size(new_shape) - 1, 1).bit_length()
+        k2, v2 = self.ops.rekey_sort(got[0], got[1], [], [], 1, kbits)
+        return ShardedFlatSparray(k2, v2, new_shape, out_split, self.group, self.ops)
+
+    # ---- gather to one canonical array (tests / small results) --------------------------------------------
+    def gather(self):
+        """All ranks get the full (indices, data) as host numpy arrays."""
+        n = torch.tensor([self.nnz_local], dtype=torch.int64, device=self.indices.device)
+        ns = [torch.empty_like(n) for _ in range(self.world)]
+        dist.all_gather(ns, n, group=self.group)
+        ns = [int(t.item()) for t in ns]
+        cap = max(ns + [1])
+        pi = torch.zeros(cap, dtype=torch.int64, device=self.indices.device)
+        pv = torch.zeros(cap, dtype=self.data.dtype, device=self.indices.device)
+        pi[:self.nnz_local] = self.indices
+        pv[:self.nnz_local] = self.data
+        gi = [torch.empty_like(pi) for _ in range(self.world)]
+        gv = [torch.empty_like(pv) for _ in range(self.world)]
+        dist.all_gather(gi, pi, group=self.group)
+        dist.all_gather(gv, pv, group=self.group)
+        idx = np.concatenate([gi[r][:ns[r]].cpu().numpy() for r in range(self.world)])
+        val = np.concatenate([gv[r][:ns[r]].cpu().numpy() for r in range(self.world)])
+        return idx, val
+
+
+def _exchange_unsorted(part, out_split):
+    """All-to-all of (key, value) pairs whose keys are NOT range-partitioned by source (after a
+    re-key): the pairs are bucketed by destination with one stable sort pass on the
+    destination id, exchanged, and returned unsorted (the caller sorts locally)."""
+    ops, group = part.ops, part.group
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    keys, vals = part.indices, part.data
+    dev = keys.device
+    bounds = torch.tensor(out_split[1:-1], dtype=torch.int64, device=dev)
+    # destination of every pair = number of boundaries <= key: keys are sorted locally after the
+    # caller's reduce / (for transpose) not sorted -- so sort them first by the full key
+    kbits = max(int(out_split[-1]) - 1, 1).bit_length()
+    keys, vals = ops.rekey_sort(keys, vals, [], [], 1, kbits)
+    full = torch.tensor(out_split, dtype=torch.int64, device=dev)
+    cut = ops.lower_bound(keys, full).cpu().tolist()
+    send_counts = [cut[d + 1] - cut[d] for d in range(world)]
+    counts = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+    all_counts = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    recv_counts = [int(all_counts[s][rank].item()) for s in range(world)]
+    recv_idx = torch.empty(sum(recv_counts), dtype=torch.int64, device=dev)
+    recv_val = torch.empty(sum(recv_counts), dtype=vals.dtype, device=dev)
+    dist.all_to_all_single(recv_idx, keys.contiguous(), recv_counts, send_counts, group=group)
+    dist.all_to_all_single(recv_val, vals.contiguous(), recv_counts, send_counts, group=group)
+    return recv_idx, recv_val
+
+
+def scatter_from_full(indices, data, shape, splitters=None, group=None, ops=None, device=None):
+    """Build this rank's shard from a full canonical array that every rank holds on the host
+    (test / ingest helper)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if splitters is None:
+        splitters = even_splitters(shape, world)
+    lo = int(np.searchsorted(indices, splitters[rank], side="left"))
+    hi = int(np.searchsorted(indices, splitters[rank + 1], side="left"))
+    dev = device if device is not None else (ops.device() if ops is not None else CudaOps().device())
+    return ShardedFlatSparray(torch.from_numpy(np.ascontiguousarray(indices[lo:hi])).to(dev),
+                              torch.from_numpy(np.ascontiguousarray(data[lo:hi])).to(dev), shape, splitters, group, ops)
