@@ -14,6 +14,15 @@ def _empty(n, dtype, like):
     return torch.empty(int(n), dtype=dtype, device=like.device)
 
 
+def _trim(t, n):
+    """First n elements of a worst-case-sized output.  When most of the buffer is unused the
+    slice is copied so the big allocation goes straight back to the caching allocator (the
+    reference's `c[:end]` views pin their full buffers)."""
+    if n * 2 < t.numel():
+        return t[:n].clone()
+    return t[:n]
+
+
 def _count(t):
     """Read a device int64 count (the one host sync of an op with a data-dependent size)."""
     return int(t.item())
@@ -108,7 +117,7 @@ def setop_binop(kind, op, a_idx, a_val, b_idx, b_val):
     check(fn(dt.BINOPS[op], dt.spb_dtype(a_val.dtype), ptr(a_idx), ptr(a_val), na, ptr(b_idx), ptr(b_val), nb,
              ptr(out_idx), ptr(out_val), ptr(cnt), workspace(), stream()))
     n = _count(cnt)
-    out_idx, out_val = out_idx[:n], out_val[:n]
+    out_idx, out_val = _trim(out_idx, n), _trim(out_val, n)
     if orig in _WIDEN and op not in dt.COMPARISONS:
         out_val = cast(out_val, orig)
     return out_idx, out_val
@@ -188,7 +197,7 @@ def select_pairs(idx, val, keep):
     check(lib.spb_select_flagged(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), ptr(keep), n, ptr(out_idx),
                                  ptr(out_val), ptr(cnt), workspace(), stream()))
     k = _count(cnt)
-    return out_idx[:k], out_val[:k]
+    return _trim(out_idx, k), _trim(out_val, k)
 
 
 def min_max(data, which):
@@ -213,7 +222,7 @@ def reduce_by_key(keys, vals, divisor=1):
     check(lib.spb_reduce_by_key(dt.spb_dtype(vals.dtype), ptr(keys), ptr(vals), n, int(divisor), ptr(out_keys),
                                 ptr(out_sums), ptr(cnt), workspace(), stream()))
     k = _count(cnt)
-    return out_keys[:k], out_sums[:k]
+    return _trim(out_keys, k), _trim(out_sums, k)
 
 
 def spmv(idx, val, ncols, nrows, x, vdtype):

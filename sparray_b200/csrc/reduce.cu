@@ -70,7 +70,7 @@ struct ReduceParams {
 __device__ __forceinline__ int pad8(int e) { return e + (e >> 3); }
 
 template <typename T, bool MULX, bool DENSE>
-__global__ void __launch_bounds__(kRNT) reduce_by_key_kernel(const ReduceParams p) {
+__global__ void __launch_bounds__(kRNT, 4) reduce_by_key_kernel(const ReduceParams p) {
     __shared__ int64_t s_key[kRTile + kRTile / 8];
     __shared__ T s_val[kRTile + kRTile / 8];
     __shared__ int64_t s_first_seg[kRNT + 1];     // first segment key of each thread (+ next tile's)
@@ -364,6 +364,14 @@ int launch_reduce(ReduceParams& p, spb_workspace* ws, cudaStream_t stream) {
     if (rc) return rc;
     p.agg_val = reinterpret_cast<double*>(ws->payload);
     p.pre_val = p.agg_val + ntiles;
+    {
+        static bool configured = false;
+        if (!configured) {   // let the SM give this kernel all the shared memory it can use
+            SPB_CUDA_TRY(cudaFuncSetAttribute(reduce_by_key_kernel<T, MULX, DENSE>,
+                                              cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            configured = true;
+        }
+    }
     reduce_by_key_kernel<T, MULX, DENSE><<<(unsigned)ntiles, kRNT, 0, stream>>>(p);
     SPB_LAUNCHED(1);
     return (int)cudaGetLastError();

@@ -103,6 +103,15 @@ struct SetopParams {
     int64_t ntiles;
     uint32_t epoch;
     int op;
+    // intersections only: outputs are rare, so a tile RESERVES its output slots with one atomic and a
+    // small second pass puts the chunks in tile order -- no cross-tile look-back at all
+    unsigned long long* slot_counter;
+    int64_t* tile_slot;      // [ntiles]
+    int* tile_cnt;           // [ntiles]
+    int64_t* tmp_idx;        // chunked outputs, min(na, nb) slots each
+    void* tmp_val;
+    int64_t* tmp_apos;
+    int64_t* tmp_bpos;
     int debug;           // SPB_DEBUG experiments (timing only; results are wrong when set)
     int negate_b;        // a - b is evaluated as a + (-b), base.py:45-46: a missing partner is +0, not -0
 };
@@ -135,6 +144,8 @@ struct PartitionParams {
     uint64_t* desc;          // [ntiles][kDescWords]
 };
 
+constexpr int64_t kGuessWindow = 8192;
+
 // 16 lanes per diagonal (two diagonals per warp): ~6 dependent rounds of 16 probe pairs each
 __global__ void __launch_bounds__(256) merge_splits_kernel(const PartitionParams p, int64_t* __restrict__ splits) {
     const int64_t gthread = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -148,6 +159,23 @@ __global__ void __launch_bounds__(256) merge_splits_kernel(const PartitionParams
     if (d > total) d = total;
     int64_t lo = d > p.nb ? d - p.nb : 0;
     int64_t hi = d < p.na ? d : p.na;
+    // Bracket around the proportional guess first: two probes instead of two rounds of 16, and --
+    // more important -- the tile boundaries stop hammering the same few top-level keys (all ~10^4
+    // searches would otherwise hit the same 32 cache lines in their first round).
+    if (hi - lo > 4 * kGuessWindow) {
+        const int64_t guess = (int64_t)(((unsigned __int128)(uint64_t)d * (uint64_t)p.na) / (uint64_t)total);
+        int64_t lo2 = guess - kGuessWindow, hi2 = guess + kGuessWindow;
+        if (lo2 < lo) lo2 = lo;
+        if (hi2 > hi) hi2 = hi;
+        bool ok = true;
+        if (lane16 == 0 && lo2 > lo) ok = __ldg(p.a + lo2 - 1) <= __ldg(p.b + (d - lo2));        // answer >= lo2
+        if (lane16 == 1 && hi2 < hi) ok = !(__ldg(p.a + hi2) <= __ldg(p.b + (d - 1 - hi2)));     // answer <= hi2
+        const unsigned okb = (__ballot_sync(gmask, ok) >> (threadIdx.x & 16)) & 0xffffu;
+        if (okb == 0xffffu) {
+            lo = lo2;
+            hi = hi2;
+        }
+    }
     while (lo < hi) {
         const int64_t span = hi - lo;
         const int64_t m = lo + ((span >> 4) * lane16) + (((span & 15) * lane16) >> 4);   // floor(span * lane / 16)
@@ -489,8 +517,17 @@ __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMi
     }
     int off = wofs + incl - cnt;
 
-    // ---- publish the count, then look back (warp 0) while the other warps materialise -----------
-    if (warp == 0) {
+    // ---- where do this tile's outputs go? ---------------------------------------------------------
+    if constexpr (KIND == KIND_INTERSECT) {
+        // reserve slots (any order); merge_reorder_kernel moves the chunks into tile order
+        if (tid == 0) {
+            const int64_t slot = (int64_t)atomicAdd(p.slot_counter, (unsigned long long)tile_total);
+            p.tile_slot[tile] = slot;
+            p.tile_cnt[tile] = tile_total;
+            *base_s = slot;
+        }
+    } else if (warp == 0) {
+        // publish the count, then look back while the other warps materialise
         uint64_t b = 0;
         if (tile == 0) {
             if (lane == 0) st_state(p.state, pack_state(kStPrefix, p.epoch, (uint64_t)tile_total));
@@ -550,18 +587,57 @@ __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMi
     }
     __syncthreads();                                                   // (D) staging + offset visible
     const int64_t base = *base_s;
+    int64_t* const o_idx = KIND == KIND_INTERSECT ? p.tmp_idx : p.out_idx;
+    VO* const o_val = reinterpret_cast<VO*>(KIND == KIND_INTERSECT ? p.tmp_val : p.out_val);
     for (int i = tid; i < ((p.debug & 4) ? 0 : tile_total); i += kNT) {
+        o_idx[base + i] = skey[i];
+        if constexpr (HAS_VAL) o_val[base + i] = sval[i];
         if constexpr (SEAM && KIND == KIND_INTERSECT) {
-            p.out_idx[base + i] = skey[i];
-            if (p.a_pos) p.a_pos[base + i] = spa[i];
-            if (p.b_pos) p.b_pos[base + i] = spb_[i];
-        } else {
-            p.out_idx[base + i] = skey[i];
-            if constexpr (HAS_VAL) reinterpret_cast<VO*>(p.out_val)[base + i] = sval[i];
-            if constexpr (SEAM && KIND == KIND_UNION) {
-                if (p.lut) p.lut[base + i] = slut[i];
-            }
+            p.tmp_apos[base + i] = spa[i];
+            p.tmp_bpos[base + i] = spb_[i];
         }
+        if constexpr (SEAM && KIND == KIND_UNION) {
+            if (p.lut) p.lut[base + i] = slut[i];
+        }
+    }
+}
+
+// ---- intersections: put the reserved chunks in tile order -----------------------------------------
+// One warp per tile, 8 tiles per CTA.  Every CTA first sums the counts of all earlier tiles itself
+// (the count array is a few tens of KB and L2-resident), which is cheaper than a separate scan launch.
+template <int VBYTES>
+__global__ void __launch_bounds__(256) merge_reorder_kernel(const SetopParams p) {
+    __shared__ int64_t s_part[8];
+    __shared__ int s_cnt[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t first_tile = (int64_t)blockIdx.x * 8;
+    int64_t acc = 0;
+    for (int64_t t = tid; t < first_tile; t += 256) acc += __ldg(p.tile_cnt + t);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const int64_t t = first_tile + warp;
+    const int n = t < p.ntiles ? p.tile_cnt[t] : 0;
+    if (lane == 0) {
+        s_part[warp] = acc;
+        s_cnt[warp] = n;
+    }
+    __syncthreads();
+    int64_t d = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        d += s_part[w];
+        if (w < warp) d += s_cnt[w];
+    }
+    if (t >= p.ntiles) return;
+    if (t == p.ntiles - 1 && lane == 0) *p.out_count = d + n;
+    const int64_t src = p.tile_slot[t];
+    for (int i = lane; i < n; i += 32) {
+        p.out_idx[d + i] = p.tmp_idx[src + i];
+        if (VBYTES == 1) reinterpret_cast<uint8_t*>(p.out_val)[d + i] = reinterpret_cast<const uint8_t*>(p.tmp_val)[src + i];
+        if (VBYTES == 4) reinterpret_cast<uint32_t*>(p.out_val)[d + i] = reinterpret_cast<const uint32_t*>(p.tmp_val)[src + i];
+        if (VBYTES == 8) reinterpret_cast<uint64_t*>(p.out_val)[d + i] = reinterpret_cast<const uint64_t*>(p.tmp_val)[src + i];
+        if (p.a_pos) p.a_pos[d + i] = p.tmp_apos[src + i];
+        if (p.b_pos) p.b_pos[d + i] = p.tmp_bpos[src + i];
     }
 }
 
@@ -576,8 +652,19 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
     int rc = workspace_reserve(ws, (size_t)ntiles * sizeof(uint64_t), stream);
     if (rc) return rc;
-    rc = workspace_reserve_payload(ws, (size_t)ntiles * kDescWords * sizeof(uint64_t) + (size_t)(ntiles + 1) * 8, stream);
-    if (rc) return rc;
+    // payload: descriptors | splits | (intersections) tile_slot, tile_dst, tile_cnt, counter, chunked outputs
+    const size_t cap = (size_t)(p.na < p.nb ? p.na : p.nb);
+    size_t off_splits = (size_t)ntiles * kDescWords * 8;
+    size_t off_slot = off_splits + (size_t)(ntiles + 1) * 8;
+    size_t off_dst = off_slot + (size_t)ntiles * 8;
+    size_t off_cnt = off_dst + (size_t)ntiles * 8;
+    size_t off_counter = (off_cnt + (size_t)ntiles * 4 + 15) & ~(size_t)15;
+    size_t off_tidx = off_counter + 16;
+    size_t off_tval = off_tidx + cap * 8;
+    size_t off_tapos = off_tval + cap * 8;
+    size_t off_tbpos = off_tapos + (SEAM ? cap * 8 : 0);
+    size_t payload_bytes = KIND == KIND_INTERSECT ? off_tbpos + (SEAM ? cap * 8 : 0) : off_slot;
+    rc = workspace_reserve_payload(ws, payload_bytes, stream);
     rc = workspace_next_epoch(ws, stream, &p.epoch);
     if (rc) return rc;
     p.state = ws_state(ws);
@@ -600,13 +687,30 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     pp.val_esize = Cfg<V, VO, KIND, HAS_VAL, SEAM>::kStageVals ? (int)sizeof(V) : 0;
     pp.ntiles = ntiles;
     pp.desc = reinterpret_cast<uint64_t*>(ws->payload);
-    int64_t* splits = reinterpret_cast<int64_t*>(pp.desc + ntiles * kDescWords);
+    char* pay = reinterpret_cast<char*>(ws->payload);
+    int64_t* splits = reinterpret_cast<int64_t*>(pay + off_splits);
+    if (KIND == KIND_INTERSECT) {
+        p.tile_slot = reinterpret_cast<int64_t*>(pay + off_slot);
+        p.tile_cnt = reinterpret_cast<int*>(pay + off_cnt);
+        p.slot_counter = reinterpret_cast<unsigned long long*>(pay + off_counter);
+        p.tmp_idx = reinterpret_cast<int64_t*>(pay + off_tidx);
+        p.tmp_val = pay + off_tval;
+        p.tmp_apos = reinterpret_cast<int64_t*>(pay + off_tapos);
+        p.tmp_bpos = reinterpret_cast<int64_t*>(pay + off_tbpos);
+        SPB_CUDA_TRY(cudaMemsetAsync(p.slot_counter, 0, 8, stream));
+    }
     merge_splits_kernel<<<(unsigned)ceil_div((ntiles + 1) * 16, 256), 256, 0, stream>>>(pp, splits);
     SPB_LAUNCHED(1);
     merge_partition_kernel<<<(unsigned)ceil_div(ntiles, 256), 256, 0, stream>>>(pp, splits);
     SPB_LAUNCHED(1);
     kern<<<(unsigned)ntiles, kThreads, smem, stream>>>(p);
     SPB_LAUNCHED(1);
+    if (KIND == KIND_INTERSECT) {
+        const unsigned rblocks = (unsigned)ceil_div(ntiles, 8);
+        constexpr int VBY = HAS_VAL ? (int)sizeof(VO) : 0;
+        merge_reorder_kernel<VBY><<<rblocks, 256, 0, stream>>>(p);
+        SPB_LAUNCHED(1);
+    }
     return (int)cudaGetLastError();
 }
 

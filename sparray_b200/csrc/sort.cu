@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) radix_scan_kernel(uint64_t* hist) {
 
 // ---- one digit pass -----------------------------------------------------------------------------
 template <typename V, bool HAS_VAL>
-__global__ void __launch_bounds__(kSNT) radix_pass_kernel(const SortParams p) {
+__global__ void __launch_bounds__(kSNT, 3) radix_pass_kernel(const SortParams p) {
     __shared__ int64_t s_keys[kSTile];                 // keys, then values, in digit-sorted tile order
     __shared__ uint8_t s_dig[kSTile];
     __shared__ unsigned s_whist[kSWarps][256];
@@ -311,6 +311,14 @@ int run_sort(SortParams p, int sort_bits, int64_t* tmp_keys, void* tmp_vals, spb
     radix_scan_kernel<<<npasses, 256, 0, stream>>>(p.hist);
     SPB_LAUNCHED(1);
     const bool has_val = p.vals_in != nullptr;
+    {
+        static bool configured = false;
+        if (!configured) {   // 47 KB static shared memory per CTA: ask for the full carve-out
+            SPB_CUDA_TRY(cudaFuncSetAttribute(radix_pass_kernel<V, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            SPB_CUDA_TRY(cudaFuncSetAttribute(radix_pass_kernel<V, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            configured = true;
+        }
+    }
     for (int ps = 0; ps < npasses; ++ps) {
         const bool to_final = ((npasses - 1 - ps) % 2) == 0;
         p.keys_out = to_final ? final_keys : tmp_keys;
