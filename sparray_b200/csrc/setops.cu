@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(256) merge_splits_kernel(const PartitionParams
 }
 
 __global__ void __launch_bounds__(256) merge_partition_kernel(const PartitionParams p, const int64_t* __restrict__ splits) {
+    cudaGridDependencySynchronize();               // splits come from the previous launch
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= p.ntiles) return;
     constexpr int kKeyReg = (kTile + 4) * 8 + 128 + kVT * 8;
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMi
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int64_t tile = blockIdx.x;
+    cudaGridDependencySynchronize();               // descriptors come from the previous launch
 
     if (warp == 0) {
         // ---- stage the tile: descriptor -> TMA bulk copies, ragged edges, sentinels -------------
@@ -611,6 +613,7 @@ __global__ void __launch_bounds__(256) merge_reorder_kernel(const SetopParams p)
     __shared__ int s_cnt[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t first_tile = (int64_t)blockIdx.x * 8;
+    cudaGridDependencySynchronize();               // chunks and counts come from the previous launch
     int64_t acc = 0;
     for (int64_t t = tid; t < first_tile; t += 256) acc += __ldg(p.tile_cnt + t);
 #pragma unroll
@@ -701,14 +704,15 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     }
     merge_splits_kernel<<<(unsigned)ceil_div((ntiles + 1) * 16, 256), 256, 0, stream>>>(pp, splits);
     SPB_LAUNCHED(1);
-    merge_partition_kernel<<<(unsigned)ceil_div(ntiles, 256), 256, 0, stream>>>(pp, splits);
+    SPB_CUDA_TRY(launch_pdl(merge_partition_kernel, dim3((unsigned)ceil_div(ntiles, 256)), dim3(256), 0, stream, pp,
+                            (const int64_t*)splits));
     SPB_LAUNCHED(1);
-    kern<<<(unsigned)ntiles, kThreads, smem, stream>>>(p);
+    SPB_CUDA_TRY(launch_pdl(kern, dim3((unsigned)ntiles), dim3(kThreads), (size_t)smem, stream, p));
     SPB_LAUNCHED(1);
     if (KIND == KIND_INTERSECT) {
         const unsigned rblocks = (unsigned)ceil_div(ntiles, 8);
         constexpr int VBY = HAS_VAL ? (int)sizeof(VO) : 0;
-        merge_reorder_kernel<VBY><<<rblocks, 256, 0, stream>>>(p);
+        SPB_CUDA_TRY(launch_pdl(merge_reorder_kernel<VBY>, dim3(rblocks), dim3(256), 0, stream, p));
         SPB_LAUNCHED(1);
     }
     return (int)cudaGetLastError();
