@@ -90,9 +90,16 @@ def check(rc):
         raise SparrayB200Error("libsparray_b200: %s (code %d)" % (msg.decode() if msg else "?", rc))
 
 
+_cuda_ok = False
+
+
 def require_cuda():
+    global _cuda_ok
+    if _cuda_ok:
+        return
     if not torch.cuda.is_available():
         raise SparrayB200Error("sparray_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    _cuda_ok = True
 
 
 def ptr(t):
@@ -102,8 +109,13 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def _raw_stream():
+    # torch.cuda.current_stream() costs ~10 us of Python per call; this is the same handle
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+
+
 def stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(_raw_stream())
 
 
 _ws_lock = threading.Lock()
@@ -112,11 +124,13 @@ _workspaces = {}
 
 def workspace():
     """One scratch workspace per (device, stream)."""
-    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
-    with _ws_lock:
-        ws = _workspaces.get(key)
-        if ws is None:
-            handle = c_p()
-            check(lib.spb_workspace_create(ctypes.byref(handle)))
-            ws = _workspaces[key] = handle
+    key = (torch._C._cuda_getDevice(), _raw_stream())
+    ws = _workspaces.get(key)
+    if ws is None:
+        with _ws_lock:
+            ws = _workspaces.get(key)
+            if ws is None:
+                handle = c_p()
+                check(lib.spb_workspace_create(ctypes.byref(handle)))
+                ws = _workspaces[key] = handle
     return ws

@@ -208,17 +208,30 @@ __global__ void __launch_bounds__(kSNT, 3) radix_pass_kernel(const SortParams p)
 
         uint64_t excl = 0;
         if (tile > 0) {
+            // per-digit look-back; the words of 8 predecessor tiles are requested together so the walk
+            // costs one round trip per 8 tiles instead of one per tile
             int64_t t = tile - 1;
-            for (;;) {
-                uint64_t w;
-                for (;;) {
-                    w = ld_state(p.state + t * 256 + d);
-                    if ((w >> 62) != 0 && (uint32_t)((w >> 48) & ((1u << kEpochBits) - 1)) == p.epoch) break;
-                    __nanosleep(20);
+            bool done = false;
+            while (!done && t >= 0) {
+                uint64_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int64_t tt = t - j;
+                    w[j] = tt >= 0 ? ld_state(p.state + tt * 256 + d) : pack_state(kStPrefix, p.epoch, 0);
                 }
-                excl += w & kCountMask;
-                if ((w >> 62) == kStPrefix || t == 0) break;
-                --t;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (!done) {
+                        const int64_t tt = t - j;
+                        while ((w[j] >> 62) == 0 || (uint32_t)((w[j] >> 48) & ((1u << kEpochBits) - 1)) != p.epoch) {
+                            __nanosleep(20);
+                            w[j] = ld_state(p.state + tt * 256 + d);
+                        }
+                        excl += w[j] & kCountMask;
+                        done = (w[j] >> 62) == kStPrefix;
+                    }
+                }
+                t -= 8;
             }
             st_state(st, pack_state(kStPrefix, p.epoch, excl + sum));
         }

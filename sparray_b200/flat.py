@@ -42,11 +42,13 @@ _FIXED_POINT_AT_ZERO = ("sin", "tan", "arcsin", "arctan", "sinh", "tanh", "arcsi
 
 def _device():
     _k.require_cuda()
-    return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cuda", torch._C._cuda_getDevice())
 
 
 def _to_device(x, dtype=None):
     """numpy / list / torch (any device) -> contiguous 1-D tensor on the current CUDA device."""
+    if isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 1 and x.is_contiguous() and (dtype is None or x.dtype == dtype):
+        return x                                   # the common internal case: already a device vector
     dev = _device()
     if isinstance(x, torch.Tensor):
         t = x.to(dev)
