@@ -1,0 +1,28 @@
+"""Event-timed API-level medians of the non-merge ops on config-shaped operands (used with
+SPB_DEBUG for elimination timing).  Usage: python profiles/time_ops.py"""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import sparray_b200 as sp
+from sparray_b200 import _kernels as k
+from run_kernels import synth
+
+def t(fn, reps=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    return np.median(ts) * 1e3
+
+shape = (256, 256, 256, 64)
+ai, av = synth(10_700_000, 256 * 256 * 256 * 64, torch.float32, 1)
+A = sp.FlatSparray(ai, av, shape=shape, is_canonical=True)
+print("SPB_DEBUG=%s" % os.environ.get("SPB_DEBUG", "0"))
+print("sum_axis3 (last) f32 10.7M: %.0f us" % t(lambda: A.sum(axis=3)))
+print("sum_axis2 f32 10.7M: %.0f us" % t(lambda: A.sum(axis=2)))
+print("transpose 3210 f32 10.7M: %.0f us" % t(lambda: A.transpose(3, 2, 1, 0)))
+wi, wv = synth(100_000_000, 10 ** 12, torch.float64, 4)
+W = sp.FlatSparray(wi, wv, shape=(10 ** 6, 10 ** 6), is_canonical=True)
+print("sum_axis1 f64 100M: %.0f us" % t(lambda: W.sum(axis=1), reps=5))

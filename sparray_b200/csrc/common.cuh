@@ -27,6 +27,8 @@ struct spb_workspace {
     int device;
     void* payload;        // plain data that rides along with the look-back (never read as state)
     size_t payload_bytes;
+    void* state16;        // 16-byte {tagged word, value} look-back entries (only ever written as such)
+    size_t state16_bytes;
 };
 
 namespace spb {
@@ -42,6 +44,7 @@ constexpr size_t kWsMiscBytes = 1u << 20;
 int workspace_reserve(spb_workspace* ws, size_t state_bytes, cudaStream_t stream);   // workspace.cu
 int workspace_next_epoch(spb_workspace* ws, cudaStream_t stream, uint32_t* epoch);
 int workspace_reserve_payload(spb_workspace* ws, size_t bytes, cudaStream_t stream);
+int workspace_reserve_state16(spb_workspace* ws, size_t bytes, cudaStream_t stream);
 int device_sm_count();
 inline uint64_t* ws_state(spb_workspace* ws) { return reinterpret_cast<uint64_t*>((char*)ws->dev + kWsMiscBytes); }
 inline char* ws_misc(spb_workspace* ws) { return (char*)ws->dev; }

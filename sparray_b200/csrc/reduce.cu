@@ -13,6 +13,8 @@
 // carries (number of segment heads, open-segment partial sum) across tiles.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace spb {
 
 constexpr int kRNT = 256;
@@ -35,6 +37,21 @@ __device__ __forceinline__ double ld_cg_f64(const double* p) {
     double v;
     asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
+}
+
+// {tagged look-back word, partial sum} travel together in one aligned 16-byte access
+struct alignas(16) Entry16 {
+    uint64_t w;
+    double v;
+};
+__device__ __forceinline__ void st_entry(Entry16* p, uint64_t w, double v) {
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w), "l"(__double_as_longlong(v)) : "memory");
+}
+__device__ __forceinline__ void ld_entry(const Entry16* p, uint64_t& w, double& v) {
+    unsigned long long a, b;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    w = a;
+    v = __longlong_as_double((long long)b);
 }
 
 struct Carry {       // (heads, open partial sum, any head) -- the scan operand
@@ -60,9 +77,7 @@ struct ReduceParams {
     int64_t* out_keys;      // compact output
     double* out_sums;       // compact (or dense: y[seg])
     int64_t* out_count;
-    uint64_t* state;        // [ntiles]
-    double* agg_val;        // [ntiles]
-    double* pre_val;        // [ntiles]
+    Entry16* entries;       // [ntiles] look-back entries
     uint32_t epoch;
 };
 
@@ -186,16 +201,36 @@ __global__ void __launch_bounds__(kRNT, 4) reduce_by_key_kernel(const ReducePara
     if (lane == 0) lane_excl = Carry{0, 0.0, false};
     Carry excl = combine(wpre, lane_excl);      // everything in this tile before my first item
 
+    if constexpr (DENSE) {
+        // Dense output (SpMV): no output compaction, so no cross-tile look-back at all.  A row that is
+        // wholly inside this tile is stored; the pieces of a row that crosses a tile border are added
+        // atomically into the zero-initialised y (at most two such rows per tile).
+        double* y = p.out_sums;
+#pragma unroll
+        for (int k = 0; k < kRVT; ++k) {
+            if (k < cnt) {
+                const bool tile_last = first + k == tile_items - 1;
+                const int64_t nxt = (k + 1 < cnt) ? seg[k + 1] : after;
+                if (nxt != seg[k] || tile_last) {
+                    const bool inside_start = (head_bits & ((2u << k) - 1u)) != 0 || excl.flag;
+                    const bool continues = tile_last && after == seg[k];
+                    const double total = (head_bits & ((2u << k) - 1u)) ? incl[k] : excl.val + incl[k];
+                    if (inside_start && !continues) y[seg[k]] = total;
+                    else atomicAdd(&y[seg[k]], total);
+                }
+            }
+        }
+        return;
+    }
     // ---- decoupled look-back (warp 0) ----------------------------------------------------------
     if (warp == 0) {
         int64_t heads_before = 0;
         double carry = 0.0;
         if (tile > 0) {
-            if (lane == 0) {
-                p.agg_val[tile] = tile_agg.val;
-                st_release(p.state + tile, pack_state(kStAgg, p.epoch,
-                                                      (uint64_t)tile_agg.heads | (tile_agg.flag ? kHeadFlag : 0)));
-            }
+            if (lane == 0)
+                st_entry(p.entries + tile,
+                         pack_state(kStAgg, p.epoch, (uint64_t)tile_agg.heads | (tile_agg.flag ? kHeadFlag : 0)),
+                         tile_agg.val);
             bool val_open = true;       // still extending the open-segment sum backwards
             int64_t base = tile - 1;
             while (base >= 0) {
@@ -204,11 +239,10 @@ __global__ void __launch_bounds__(kRNT, 4) reduce_by_key_kernel(const ReducePara
                 double pv = 0.0;
                 if (t >= 0) {
                     for (;;) {
-                        w = ld_acquire(p.state + t);
+                        ld_entry(p.entries + t, w, pv);
                         if ((w >> 62) != 0 && (uint32_t)((w >> 48) & ((1u << kEpochBits) - 1)) == p.epoch) break;
                         __nanosleep(20);
                     }
-                    pv = ld_cg_f64(((w >> 62) == kStPrefix ? p.pre_val : p.agg_val) + t);
                 }
                 const unsigned has_prefix = __ballot_sync(0xffffffffu, (w >> 62) == kStPrefix);
                 const int stop = has_prefix ? (__ffs(has_prefix) - 1) : 31;
@@ -230,9 +264,9 @@ __global__ void __launch_bounds__(kRNT, 4) reduce_by_key_kernel(const ReducePara
         }
         if (lane == 0) {
             const Carry incl_prefix = combine(Carry{heads_before, carry, heads_before > 0}, tile_agg);
-            p.pre_val[tile] = incl_prefix.val;
-            st_release(p.state + tile, pack_state(kStPrefix, p.epoch,
-                                                  (uint64_t)incl_prefix.heads | (incl_prefix.flag ? kHeadFlag : 0)));
+            st_entry(p.entries + tile,
+                     pack_state(kStPrefix, p.epoch, (uint64_t)incl_prefix.heads | (incl_prefix.flag ? kHeadFlag : 0)),
+                     incl_prefix.val);
             s_tile_heads = heads_before;
             s_tile_carry = carry;
             if (!DENSE && tile_start + tile_items == p.n) *p.out_count = incl_prefix.heads;
@@ -355,15 +389,13 @@ template <typename T, bool MULX, bool DENSE>
 int launch_reduce(ReduceParams& p, spb_workspace* ws, cudaStream_t stream) {
     const int64_t ntiles = ceil_div(p.n, kRTile);
     if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
-    int rc = workspace_reserve(ws, (size_t)ntiles * 8, stream);
+    int rc = workspace_reserve(ws, 0, stream);
+    if (rc) return rc;
+    rc = workspace_reserve_state16(ws, (size_t)ntiles * sizeof(Entry16), stream);
     if (rc) return rc;
     rc = workspace_next_epoch(ws, stream, &p.epoch);
     if (rc) return rc;
-    p.state = ws_state(ws);
-    rc = workspace_reserve_payload(ws, (size_t)ntiles * 8 * 2, stream);
-    if (rc) return rc;
-    p.agg_val = reinterpret_cast<double*>(ws->payload);
-    p.pre_val = p.agg_val + ntiles;
+    p.entries = reinterpret_cast<Entry16*>(ws->state16);
     {
         static bool configured = false;
         if (!configured) {   // let the SM give this kernel all the shared memory it can use

@@ -158,12 +158,8 @@ __global__ void __launch_bounds__(kSNT, 3) radix_pass_kernel(const SortParams p)
         const bool valid = e < items;
         const unsigned d = (unsigned)(sort_key(keys[k], p) >> p.shift) & 255u;
         dig[k] = (uint8_t)d;
-        unsigned peers = __ballot_sync(0xffffffffu, valid);
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
-            peers &= ((d >> b) & 1u) ? bal : ~bal;
-        }
+        // lanes holding the same digit (invalid lanes get a private value): one MATCH instead of 8 votes
+        unsigned peers = __match_any_sync(0xffffffffu, valid ? d : (0x100u | (unsigned)lane));
         if (!valid) peers = 0;
         const int leader = peers ? (__ffs(peers) - 1) : lane;
         unsigned old = 0;

@@ -37,11 +37,28 @@ int workspace_reserve_payload(spb_workspace* ws, size_t bytes, cudaStream_t stre
     return SPB_OK;
 }
 
+int workspace_reserve_state16(spb_workspace* ws, size_t bytes, cudaStream_t stream) {
+    if (!ws) return SPB_ERR_BAD_ARG;
+    if (ws->state16_bytes >= bytes && ws->state16) return SPB_OK;
+    if (ws->state16) {
+        SPB_CUDA_TRY(cudaStreamSynchronize(stream));
+        SPB_CUDA_TRY(cudaFree(ws->state16));
+        ws->state16 = nullptr;
+        ws->state16_bytes = 0;
+    }
+    const size_t want = bytes + bytes / 2 + (1u << 20);
+    SPB_CUDA_TRY(cudaMalloc(&ws->state16, want));
+    SPB_CUDA_TRY(cudaMemsetAsync(ws->state16, 0, want, stream));   // zero words read as "invalid" in every epoch
+    ws->state16_bytes = want;
+    return SPB_OK;
+}
+
 // next launch epoch (1 .. 2^14-1); re-zero the state words when the counter wraps
 int workspace_next_epoch(spb_workspace* ws, cudaStream_t stream, uint32_t* epoch) {
     ws->epoch += 1;
     if (ws->epoch >= (1u << kEpochBits)) {
         SPB_CUDA_TRY(cudaMemsetAsync(ws->dev, 0, ws->bytes, stream));
+        if (ws->state16) SPB_CUDA_TRY(cudaMemsetAsync(ws->state16, 0, ws->state16_bytes, stream));
         ws->epoch = 1;
     }
     *epoch = ws->epoch;
@@ -74,6 +91,8 @@ int spb_workspace_create(spb_workspace** ws) {
     w->device = dev;
     w->payload = nullptr;
     w->payload_bytes = 0;
+    w->state16 = nullptr;
+    w->state16_bytes = 0;
     *ws = w;
     return SPB_OK;
 }
@@ -82,6 +101,7 @@ int spb_workspace_destroy(spb_workspace* ws) {
     if (!ws) return SPB_OK;
     if (ws->dev) cudaFree(ws->dev);
     if (ws->payload) cudaFree(ws->payload);
+    if (ws->state16) cudaFree(ws->state16);
     delete ws;
     return SPB_OK;
 }
