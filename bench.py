@@ -39,6 +39,10 @@ SHAPE = (256, 256, 256, 64)
 DENSITY = 0.01
 DTYPE = np.float32
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+# ncu --set full capture of this workload (profiles/README.md); None until a capture exists
+NCU_TRAFFIC_BYTES = None
+NCU_TRAFFIC_SOURCE = None
 
 
 def load_oracle():
@@ -70,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -269,8 +273,10 @@ def main():
     alg_bytes = (na + nb) * 8 + nout * (4 + 4) + nout * (8 + 4)
     peak, peak_src = hbm_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "setop_kernel<float,float,INTERSECT> (spb_intersect_binop)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm", "kernel": "spb_intersect_binop = merge_splits + merge_partition + "
+                                          "setop_kernel<float,float,INTERSECT> + merge_reorder (4 launches)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "peak_source": peak_src,
                 "timing": "CUDA events around each of %d launches on the launch stream; 256 MB of operands > 126 MB L2" % reps}
 

@@ -121,6 +121,7 @@ enum { KIND_UNION = 0, KIND_INTERSECT = 1 };
 constexpr int kNT = 256;   // threads per CTA
 constexpr int kVT = 8;     // merged items per thread
 constexpr int kTile = kNT * kVT;
+constexpr int kFixedSlots = 64;   // intersection: private output slots per tile before the overflow area
 
 // ---- launch 1: merge-path split of every tile + its staging descriptor ------------------------
 // One warp per tile: two 32-ary merge-path searches (the tile's two diagonals), then lane 0
@@ -521,9 +522,13 @@ __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMi
 
     // ---- where do this tile's outputs go? ---------------------------------------------------------
     if constexpr (KIND == KIND_INTERSECT) {
-        // reserve slots (any order); merge_reorder_kernel moves the chunks into tile order
+        // Every tile owns kFixedSlots output slots outright (matches are rare: no round trip at all);
+        // a tile with more matches reserves room in the overflow area with one atomic.
+        // merge_reorder_kernel moves the chunks into tile order.
         if (tid == 0) {
-            const int64_t slot = (int64_t)atomicAdd(p.slot_counter, (unsigned long long)tile_total);
+            int64_t slot = tile * kFixedSlots;
+            if (tile_total > kFixedSlots)
+                slot = p.ntiles * kFixedSlots + (int64_t)atomicAdd(p.slot_counter, (unsigned long long)tile_total);
             p.tile_slot[tile] = slot;
             p.tile_cnt[tile] = tile_total;
             *base_s = slot;
@@ -656,7 +661,7 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     int rc = workspace_reserve(ws, (size_t)ntiles * sizeof(uint64_t), stream);
     if (rc) return rc;
     // payload: descriptors | splits | (intersections) tile_slot, tile_dst, tile_cnt, counter, chunked outputs
-    const size_t cap = (size_t)(p.na < p.nb ? p.na : p.nb);
+    const size_t cap = (size_t)(p.na < p.nb ? p.na : p.nb) + (size_t)ntiles * kFixedSlots;
     size_t off_splits = (size_t)ntiles * kDescWords * 8;
     size_t off_slot = off_splits + (size_t)(ntiles + 1) * 8;
     size_t off_dst = off_slot + (size_t)ntiles * 8;
