@@ -41,8 +41,10 @@ DTYPE = np.float32
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # ncu --set full capture of this workload (profiles/README.md); None until a capture exists
-NCU_TRAFFIC_BYTES = None
-NCU_TRAFFIC_SOURCE = None
+NCU_TRAFFIC_BYTES = 201036544   # 196.18 MB read + 4.86 MB written
+NCU_TRAFFIC_SOURCE = ("profiles/r1_setop_intersect_final_ncu_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum of "
+                      "setop_kernel<float,float,INTERSECT> (73 % of the call's GPU time; the partition and reorder "
+                      "launches were not captured with --set full)")
 
 
 def load_oracle():
