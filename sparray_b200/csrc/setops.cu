@@ -119,9 +119,10 @@ struct SetopParams {
 enum { KIND_UNION = 0, KIND_INTERSECT = 1 };
 
 constexpr int kNT = 256;   // threads per CTA
-constexpr int kVT = 8;     // merged items per thread
-constexpr int kTile = kNT * kVT;
-constexpr int kFixedSlots = 64;   // intersection: private output slots per tile before the overflow area
+// merged items per thread: 16 for intersections (no value staging, outputs are rare, so the tile can
+// be 4096 items and the per-thread merge-path search is amortised over twice as many items), 8 for
+// unions (values and a full tile of outputs are staged in shared memory)
+constexpr int key_region_bytes(int vt) { return (kNT * vt + 4) * 8 + 128 + vt * 8; }
 
 // ---- launch 1: merge-path split of every tile + its staging descriptor ------------------------
 // One warp per tile: two 32-ary merge-path searches (the tile's two diagonals), then lane 0
@@ -141,6 +142,8 @@ struct PartitionParams {
     const void* a_val;
     const void* b_val;
     int val_esize;           // 0: values are not staged
+    int tile_items;          // merged items per tile
+    int key_reg;             // bytes of the key region of a tile buffer
     int64_t ntiles;
     uint64_t* desc;          // [ntiles][kDescWords]
 };
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(256) merge_splits_kernel(const PartitionParams
     const bool active = w <= p.ntiles;
     if (!active) w = p.ntiles;                   // keep the half-warp converged on a valid diagonal
     const int64_t total = p.na + p.nb;
-    int64_t d = w * kTile;
+    int64_t d = w * (int64_t)p.tile_items;
     if (d > total) d = total;
     int64_t lo = d > p.nb ? d - p.nb : 0;
     int64_t hi = d < p.na ? d : p.na;
@@ -200,10 +203,10 @@ __global__ void __launch_bounds__(256) merge_partition_kernel(const PartitionPar
     cudaGridDependencySynchronize();               // splits come from the previous launch
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= p.ntiles) return;
-    constexpr int kKeyReg = (kTile + 4) * 8 + 128 + kVT * 8;
+    const int kKeyReg = p.key_reg;
     const int64_t total = p.na + p.nb;
-    const int64_t d0 = t * kTile;
-    const int64_t d1 = (d0 + kTile < total) ? d0 + kTile : total;
+    const int64_t d0 = t * (int64_t)p.tile_items;
+    const int64_t d1 = (d0 + p.tile_items < total) ? d0 + p.tile_items : total;
     const int64_t a0 = splits[t], a1 = splits[t + 1];
     const int64_t b0 = d0 - a0, b1 = d1 - a1;
     // indices [x0-1, x1] (one halo key either side), values [x0, x1) (+1 for B: partner of the last A)
@@ -268,10 +271,11 @@ struct Geom {            // where a staged tile lives inside its buffer
     int offAv, offBv;    // byte offset of Av[0] / Bv[0]
 };
 
-template <int VBYTES, int NBUF, int OUT_KEYS, int OUT_PAYLOAD>   // staged value bytes; ring depth; staging bytes
+template <int VT, int VBYTES, int NBUF, int OUT_KEYS, int OUT_PAYLOAD>   // items/thread; staged value bytes; buffers; staging bytes
 struct Layout {
+    static constexpr int kTile = kNT * VT;
     static constexpr int kHeader = 256;
-    static constexpr int kKeyReg = (kTile + 4) * 8 + 128 + kVT * 8;
+    static constexpr int kKeyReg = key_region_bytes(VT);
     static constexpr int kValReg = VBYTES ? kTile * VBYTES + 96 : 0;
     static constexpr int kBuf = kKeyReg + kValReg;                       // one staged input tile
     static constexpr int kStgKeys = OUT_KEYS;                            // compacted outputs waiting for their offset
@@ -283,12 +287,15 @@ struct Layout {
 template <typename V, typename VO, int KIND, bool HAS_VAL, bool SEAM>
 struct Cfg {
     static constexpr bool kStageVals = HAS_VAL && KIND == KIND_UNION;
+    static constexpr int kVT = KIND == KIND_UNION ? 8 : 16;
+    static constexpr int kTile = kNT * kVT;
+    static constexpr int kFixedSlots = 8 * kVT;                          // private output slots per tile (intersections)
     static constexpr int kCap = KIND == KIND_UNION ? kTile : kTile / 2;  // outputs per tile, at most
-    static constexpr int kPayload = HAS_VAL ? kCap * (int)sizeof(VO)
-                                            : (SEAM ? (KIND == KIND_UNION ? kCap : 2 * kCap * 8) : 0);
+    static constexpr int kPayload = KIND == KIND_INTERSECT ? 0
+                                    : (HAS_VAL ? kCap * (int)sizeof(VO) : (SEAM ? kCap : 0));
     static constexpr int kNBuf = 1;
     static constexpr int kMinCtas = !kStageVals ? 6 : (sizeof(V) == 8 ? 3 : 4);   // what shared memory allows   // what shared memory allows
-    using L = Layout<kStageVals ? (int)sizeof(V) : 0, kNBuf, kCap * 8, kPayload>;
+    using L = Layout<kVT, kStageVals ? (int)sizeof(V) : 0, kNBuf, KIND == KIND_INTERSECT ? 0 : kCap * 8, kPayload>;
 };
 
 struct EdgeReg {         // an unaligned head / tail element riding in a register until its buffer is live
@@ -379,7 +386,7 @@ __device__ __forceinline__ int merge_path_smem(const Acc& a, int na, const Acc& 
 // Branch-free walk of kVT merged items starting at (ai, bi): records who was taken (A or B),
 // where both sides held the same key, and which items are emitted.  Ties go to A; the B
 // partner of a matched A item is the very next item and is suppressed (prev_eq).
-template <typename Acc, int KIND>
+template <typename Acc, int KIND, int kVT>
 __device__ __forceinline__ void merge_walk(const Acc& A, const Acc& B, int ai, int bi, int steps, bool prev_eq,
                                            unsigned& m_ta, unsigned& m_eq, unsigned& m_emit) {
     auto ka = A(ai);
@@ -416,6 +423,8 @@ __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMi
     using L = typename C::L;
     constexpr bool STAGE_VALS = C::kStageVals;
     constexpr int VB = STAGE_VALS ? (int)sizeof(V) : 0;
+    constexpr int kVT = C::kVT;
+    constexpr int kFixedSlots = C::kFixedSlots;
     extern __shared__ __align__(128) char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     Geom* geom = reinterpret_cast<Geom*>(smem + 16);                    // 40 bytes
@@ -492,13 +501,13 @@ __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMi
         ai0 = merge_path_smem(A, an, B, bn, diag);
         bi0 = diag - ai0;
         const bool prev_eq = ai0 > 0 ? (A(ai0 - 1) == B(bi0)) : (bi0 == 0 && front_dup);
-        merge_walk<NarrowKeys, KIND>(A, B, ai0, bi0, steps, prev_eq, m_ta, m_eq, m_emit);
+        merge_walk<NarrowKeys, KIND, kVT>(A, B, ai0, bi0, steps, prev_eq, m_ta, m_eq, m_emit);
     } else {
         const WideKeys A{As64}, B{Bs64};
         ai0 = merge_path_smem(A, an, B, bn, diag);
         bi0 = diag - ai0;
         const bool prev_eq = ai0 > 0 ? (A(ai0 - 1) == B(bi0)) : (bi0 == 0 && front_dup);
-        merge_walk<WideKeys, KIND>(A, B, ai0, bi0, steps, prev_eq, m_ta, m_eq, m_emit);
+        merge_walk<WideKeys, KIND, kVT>(A, B, ai0, bi0, steps, prev_eq, m_ta, m_eq, m_emit);
     }
 
     // ---- block exclusive scan of the output counts -------------------------------------------
@@ -549,7 +558,19 @@ __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMi
         }
     }
 
-    // ---- materialise the emitted items straight into the staging area --------------------------
+    // ---- materialise the emitted items: unions into the shared staging area (stored coalesced
+    //      below); intersections -- few outputs -- straight to their reserved global slots -----------
+    int64_t* ek = skey;
+    VO* ev = sval;
+    int64_t *epa = spa, *epb = spb_;
+    if constexpr (KIND == KIND_INTERSECT) {
+        __syncthreads();                                               // slot of this tile visible
+        const int64_t slot = *base_s;
+        ek = p.tmp_idx + slot;
+        ev = reinterpret_cast<VO*>(p.tmp_val) + slot;
+        epa = p.tmp_apos + slot;
+        epb = p.tmp_bpos + slot;
+    }
     if (KIND == KIND_UNION || m_emit != 0) {
         const V* Av = STAGE_VALS ? reinterpret_cast<const V*>(buf + g.offAv) : nullptr;
         const V* Bv = STAGE_VALS ? reinterpret_cast<const V*>(buf + g.offBv) : nullptr;
@@ -558,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMi
         for (int k = 0; k < kVT; ++k) {
             const bool ta = (m_ta >> k) & 1u, eq = ta && ((m_eq >> k) & 1u), e = (m_emit >> k) & 1u;
             if (e) {
-                skey[off] = ta ? As64[ai] : Bs64[bi];
+                ek[off] = ta ? As64[ai] : Bs64[bi];
                 if constexpr (HAS_VAL) {
                     V x, y;
                     if constexpr (STAGE_VALS) {
@@ -570,12 +591,12 @@ __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMi
                         y = __ldg(reinterpret_cast<const V*>(p.b_val) + g.b0 + bi);
                         if (p.negate_b) y = (V)(-y);
                     }
-                    sval[off] = value_op<V, VO>(p.op, x, y);
+                    ev[off] = value_op<V, VO>(p.op, x, y);
                 }
                 if constexpr (SEAM && KIND == KIND_UNION) slut[off] = ta ? (eq ? 2 : 0) : 1;
                 if constexpr (SEAM && KIND == KIND_INTERSECT) {
-                    spa[off] = g.a0 + ai;
-                    spb_[off] = g.b0 + bi;
+                    epa[off] = g.a0 + ai;
+                    epb[off] = g.b0 + bi;
                 }
                 ++off;
             }
@@ -592,17 +613,13 @@ __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMi
             bi += ta ? 0 : ((k < steps) ? 1 : 0);
         }
     }
+    if constexpr (KIND == KIND_INTERSECT) return;
     __syncthreads();                                                   // (D) staging + offset visible
     const int64_t base = *base_s;
-    int64_t* const o_idx = KIND == KIND_INTERSECT ? p.tmp_idx : p.out_idx;
-    VO* const o_val = reinterpret_cast<VO*>(KIND == KIND_INTERSECT ? p.tmp_val : p.out_val);
+    VO* const o_val = reinterpret_cast<VO*>(p.out_val);
     for (int i = tid; i < ((p.debug & 4) ? 0 : tile_total); i += kNT) {
-        o_idx[base + i] = skey[i];
+        p.out_idx[base + i] = skey[i];
         if constexpr (HAS_VAL) o_val[base + i] = sval[i];
-        if constexpr (SEAM && KIND == KIND_INTERSECT) {
-            p.tmp_apos[base + i] = spa[i];
-            p.tmp_bpos[base + i] = spb_[i];
-        }
         if constexpr (SEAM && KIND == KIND_UNION) {
             if (p.lut) p.lut[base + i] = slut[i];
         }
@@ -656,6 +673,9 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     if (total == 0 || (KIND == KIND_INTERSECT && (p.na == 0 || p.nb == 0))) {
         return (int)cudaMemsetAsync(p.out_count, 0, sizeof(int64_t), stream);
     }
+    using C = Cfg<V, VO, KIND, HAS_VAL, SEAM>;
+    constexpr int kTile = C::kTile;
+    constexpr int kFixedSlots = C::kFixedSlots;
     const int64_t ntiles = ceil_div(total, kTile);
     if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
     int rc = workspace_reserve(ws, (size_t)ntiles * sizeof(uint64_t), stream);
@@ -694,6 +714,8 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     pp.a = p.a; pp.b = p.b; pp.na = p.na; pp.nb = p.nb; pp.a_val = p.a_val; pp.b_val = p.b_val;
     pp.val_esize = Cfg<V, VO, KIND, HAS_VAL, SEAM>::kStageVals ? (int)sizeof(V) : 0;
     pp.ntiles = ntiles;
+    pp.tile_items = kTile;
+    pp.key_reg = C::L::kKeyReg;
     pp.desc = reinterpret_cast<uint64_t*>(ws->payload);
     char* pay = reinterpret_cast<char*>(ws->payload);
     int64_t* splits = reinterpret_cast<int64_t*>(pay + off_splits);
