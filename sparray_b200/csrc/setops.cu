@@ -294,6 +294,10 @@ struct Cfg {
     static constexpr int kPayload = KIND == KIND_INTERSECT ? 0
                                     : (HAS_VAL ? kCap * (int)sizeof(VO) : (SEAM ? kCap : 0));
     static constexpr int kNBuf = 1;
+    // unions resolve their output offset by look-back: a ninth warp does it (and the staging) so that
+    // no merging warp is held up by the L2 round trips
+    static constexpr int kHelperWarp = KIND == KIND_UNION ? kNT / 32 : 0;
+    static constexpr int kThreads = KIND == KIND_UNION ? kNT + 32 : kNT;
     static constexpr int kMinCtas = !kStageVals ? 6 : (sizeof(V) == 8 ? 3 : 4);   // what shared memory allows   // what shared memory allows
     using L = Layout<kVT, kStageVals ? (int)sizeof(V) : 0, kNBuf, KIND == KIND_INTERSECT ? 0 : kCap * 8, kPayload>;
 };
@@ -412,19 +416,20 @@ __device__ __forceinline__ void merge_walk(const Acc& A, const Acc& B, int ai, i
     m_emit = (KIND == KIND_UNION ? m_emit : m_eq) & live;
 }
 
-constexpr int kThreads = kNT;
 
 // One CTA = one tile (blockIdx order, so the decoupled look-back only ever waits on tiles that
 // started earlier).  Latency is hidden across the 3-4 CTAs resident per SM: while one waits for
 // its TMA copies, others merge or store.
 template <typename V, typename VO, int KIND, bool HAS_VAL, bool SEAM>
-__global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMinCtas) setop_kernel(const SetopParams p) {
+__global__ void __launch_bounds__(Cfg<V, VO, KIND, HAS_VAL, SEAM>::kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMinCtas)
+setop_kernel(const SetopParams p) {
     using C = Cfg<V, VO, KIND, HAS_VAL, SEAM>;
     using L = typename C::L;
     constexpr bool STAGE_VALS = C::kStageVals;
     constexpr int VB = STAGE_VALS ? (int)sizeof(V) : 0;
     constexpr int kVT = C::kVT;
     constexpr int kFixedSlots = C::kFixedSlots;
+    constexpr int kHelper = C::kHelperWarp;
     extern __shared__ __align__(128) char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     Geom* geom = reinterpret_cast<Geom*>(smem + 16);                    // 40 bytes
@@ -443,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMi
     const int64_t tile = blockIdx.x;
     cudaGridDependencySynchronize();               // descriptors come from the previous launch
 
-    if (warp == 0) {
+    if (warp == kHelper) {
         // ---- stage the tile: descriptor -> TMA bulk copies, ragged edges, sentinels -------------
         const uint64_t dw = lane < kDescWords ? __ldg(p.desc + tile * kDescWords + lane) : 0;
         if (lane == 0) {
@@ -518,7 +523,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMi
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
-    if (lane == 31) warp_sums[warp] = incl;
+    if (lane == 31 && warp < kNT / 32) warp_sums[warp] = incl;
     __syncthreads();                                                   // (C)
     int wofs = 0, tile_total = 0;
 #pragma unroll
@@ -542,8 +547,8 @@ __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMi
             p.tile_cnt[tile] = tile_total;
             *base_s = slot;
         }
-    } else if (warp == 0) {
-        // publish the count, then look back while the other warps materialise
+    } else if (warp == kHelper) {
+        // publish the count, then look back while the merging warps materialise
         uint64_t b = 0;
         if (tile == 0) {
             if (lane == 0) st_state(p.state, pack_state(kStPrefix, p.epoch, (uint64_t)tile_total));
@@ -617,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMi
     __syncthreads();                                                   // (D) staging + offset visible
     const int64_t base = *base_s;
     VO* const o_val = reinterpret_cast<VO*>(p.out_val);
-    for (int i = tid; i < ((p.debug & 4) ? 0 : tile_total); i += kNT) {
+    for (int i = tid < kNT ? tid : tile_total; i < ((p.debug & 4) ? 0 : tile_total); i += kNT) {
         p.out_idx[base + i] = skey[i];
         if constexpr (HAS_VAL) o_val[base + i] = sval[i];
         if constexpr (SEAM && KIND == KIND_UNION) {
@@ -707,7 +712,7 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     if (!ctas_per_sm) {
         SPB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         SPB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        SPB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kThreads, smem));
+        SPB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, C::kThreads, smem));
         if (ctas_per_sm < 1) return SPB_ERR_UNSUPPORTED;
     }
     PartitionParams pp{};
@@ -734,7 +739,7 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     SPB_CUDA_TRY(launch_pdl(merge_partition_kernel, dim3((unsigned)ceil_div(ntiles, 256)), dim3(256), 0, stream, pp,
                             (const int64_t*)splits));
     SPB_LAUNCHED(1);
-    SPB_CUDA_TRY(launch_pdl(kern, dim3((unsigned)ntiles), dim3(kThreads), (size_t)smem, stream, p));
+    SPB_CUDA_TRY(launch_pdl(kern, dim3((unsigned)ntiles), dim3(C::kThreads), (size_t)smem, stream, p));
     SPB_LAUNCHED(1);
     if (KIND == KIND_INTERSECT) {
         const unsigned rblocks = (unsigned)ceil_div(ntiles, 8);
