@@ -417,6 +417,16 @@ __device__ __forceinline__ void merge_walk(const Acc& A, const Acc& B, int ai, i
 }
 
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// barrier among the merging warps only (unions have a ninth helper warp that must not be waited for)
+template <int KIND>
+__device__ __forceinline__ void sync_mergers() {
+    if constexpr (KIND == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else __syncthreads();
+}
+
 // One CTA = one tile (blockIdx order, so the decoupled look-back only ever waits on tiles that
 // started earlier).  Latency is hidden across the 3-4 CTAs resident per SM: while one waits for
 // its TMA copies, others merge or store.
@@ -448,14 +458,22 @@ setop_kernel(const SetopParams p) {
     const int64_t tile = blockIdx.x;
     cudaGridDependencySynchronize();               // descriptors come from the previous launch
 
+    uint64_t* agg_bar = reinterpret_cast<uint64_t*>(smem + 104);       // unions: count published -> helper
+    uint64_t* ready_bar = reinterpret_cast<uint64_t*>(smem + 112);     // unions: offset resolved -> mergers
+    int* tot_s = reinterpret_cast<int*>(smem + 120);
+    if (tid == 0) {
+        mbar_init(full, KIND == KIND_UNION ? 2 : 1);   // unions: + the helper's "edges written" arrival
+        if (KIND == KIND_UNION) {
+            mbar_init(agg_bar, 1);
+            mbar_init(ready_bar, 1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();                                                   // barriers initialised (all warps)
+
     if (warp == kHelper) {
         // ---- stage the tile: descriptor -> TMA bulk copies, ragged edges, sentinels -------------
         const uint64_t dw = lane < kDescWords ? __ldg(p.desc + tile * kDescWords + lane) : 0;
-        if (lane == 0) {
-            mbar_init(full, 1);
-            fence_mbar_init();
-        }
-        __syncwarp();
         EdgeReg er;
         prefetch_tile<VB>(dw, buf, full, geom, er, lane);
         edge_store(er);
@@ -468,8 +486,25 @@ setop_kernel(const SetopParams p) {
         if (lane == 1 && a0 + an_ == p.na) As64w[an_] = kKeyMax;
         if (lane == 2 && b0 == 0) Bs64w[-1] = kKeyMin;
         if (lane == 3 && b0 + bn_ == p.nb) Bs64w[bn_] = kKeyMax;
+        if constexpr (KIND == KIND_UNION) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full);                          // geometry, edges, sentinels are in place
+            // The exclusive prefix of the EARLIER tiles does not depend on this tile's own count, so the
+            // look-back starts now and overlaps the TMA flight and the whole merge.
+            uint64_t b = 0;
+            if (tile > 0 && !(p.debug & 1)) b = lookback_exclusive(p.state, tile, p.epoch);
+            mbar_wait(agg_bar, 0);                                     // the mergers have published the count
+            const int total = *tot_s;
+            if (lane == 0) {
+                if (tile > 0) st_state(p.state + tile, pack_state(kStPrefix, p.epoch, b + (uint64_t)total));
+                if (tile == (int64_t)gridDim.x - 1) *p.out_count = (int64_t)b + total;
+                *base_s = (int64_t)b;
+                mbar_arrive(ready_bar);
+            }
+            return;
+        }
     }
-    __syncthreads();                                                   // (A) barrier initialised, geometry / edges visible
+    if constexpr (KIND != KIND_UNION) __syncthreads();                 // (A) geometry / edges visible
     mbar_wait(full, 0);
 
     const Geom g = *geom;
@@ -490,7 +525,7 @@ setop_kernel(const SetopParams p) {
         int64_t* h = const_cast<int64_t*>(tid == 0 ? As64 + an : Bs64 + bn);
         if ((uint64_t)(*h - kbase) > 0xfffffffeull) *h = kbase + 0xffffffffll;
     }
-    __syncthreads();                                                   // (B)
+    sync_mergers<KIND>();                                              // (B)
 
     // ---- per-thread merge-path split + branch-free walk ------------------------------------
     int diag = tid * kVT;
@@ -524,7 +559,7 @@ setop_kernel(const SetopParams p) {
         if (lane >= o) incl += t;
     }
     if (lane == 31 && warp < kNT / 32) warp_sums[warp] = incl;
-    __syncthreads();                                                   // (C)
+    sync_mergers<KIND>();                                              // (C)
     int wofs = 0, tile_total = 0;
 #pragma unroll
     for (int w = 0; w < kNT / 32; ++w) {
@@ -547,20 +582,12 @@ setop_kernel(const SetopParams p) {
             p.tile_cnt[tile] = tile_total;
             *base_s = slot;
         }
-    } else if (warp == kHelper) {
-        // publish the count, then look back while the merging warps materialise
-        uint64_t b = 0;
-        if (tile == 0) {
-            if (lane == 0) st_state(p.state, pack_state(kStPrefix, p.epoch, (uint64_t)tile_total));
-        } else {
-            if (lane == 0) st_state(p.state + tile, pack_state(kStAgg, p.epoch, (uint64_t)tile_total));
-            if (!(p.debug & 1)) b = lookback_exclusive(p.state, tile, p.epoch);
-            if (lane == 0) st_state(p.state + tile, pack_state(kStPrefix, p.epoch, b + (uint64_t)tile_total));
-        }
-        if (lane == 0) {
-            *base_s = (int64_t)b;
-            if (tile == (int64_t)gridDim.x - 1) *p.out_count = (int64_t)b + tile_total;
-        }
+    } else if (tid == 0) {
+        // publish the count for the successors, and hand it to the helper warp (which has been looking
+        // back since the tile was put in flight)
+        st_state(p.state + tile, pack_state(tile == 0 ? kStPrefix : kStAgg, p.epoch, (uint64_t)tile_total));
+        *tot_s = tile_total;
+        mbar_arrive(agg_bar);
     }
 
     // ---- materialise the emitted items: unions into the shared staging area (stored coalesced
@@ -619,7 +646,8 @@ setop_kernel(const SetopParams p) {
         }
     }
     if constexpr (KIND == KIND_INTERSECT) return;
-    __syncthreads();                                                   // (D) staging + offset visible
+    sync_mergers<KIND>();                                              // (D) staging complete
+    mbar_wait(ready_bar, 0);                                           // offset resolved by the helper warp
     const int64_t base = *base_s;
     VO* const o_val = reinterpret_cast<VO*>(p.out_val);
     for (int i = tid < kNT ? tid : tile_total; i < ((p.debug & 4) ? 0 : tile_total); i += kNT) {
