@@ -40,7 +40,8 @@ enum spb_binop {
     SPB_ADD = 0, SPB_SUB = 1, SPB_MUL = 2, SPB_MINIMUM = 3, SPB_MAXIMUM = 4,
     SPB_LT = 5, SPB_LE = 6, SPB_GT = 7, SPB_GE = 8, SPB_EQ = 9, SPB_NE = 10,   /* -> bool output */
     SPB_TAKE_A = 11, SPB_TAKE_B = 12,
-    SPB_BINOP_COUNT = 13
+    SPB_OVERRIDE = 13,   /* union only: b where b is stored, else a -- _setitem_flatidx, flat.py:395-407 */
+    SPB_BINOP_COUNT = 14
 };
 
 /* unary / scalar value maps: flat.py:580-581,677-739, compat.py:96-102 */

@@ -623,7 +623,12 @@ setop_kernel(const SetopParams p) {
                         y = __ldg(reinterpret_cast<const V*>(p.b_val) + g.b0 + bi);
                         if (p.negate_b) y = (V)(-y);
                     }
-                    ev[off] = value_op<V, VO>(p.op, x, y);
+                    if constexpr (KIND == KIND_UNION && sizeof(VO) == sizeof(V)) {
+                        // assignment semantics: the stored b wins, a survives where b is absent
+                        ev[off] = p.op == SPB_OVERRIDE ? (VO)((!ta || eq) ? y : x) : value_op<V, VO>(p.op, x, y);
+                    } else {
+                        ev[off] = value_op<V, VO>(p.op, x, y);
+                    }
                 }
                 if constexpr (SEAM && KIND == KIND_UNION) slut[off] = ta ? (eq ? 2 : 0) : 1;
                 if constexpr (SEAM && KIND == KIND_INTERSECT) {

@@ -16,7 +16,7 @@ Deliberate divergences from the reference:
     queries and numpy semantics for repeated ones;
   * branches that densify (sparse + nonzero scalar, sparse / sparse, ...) and
     mixed dense-ndarray operands are out of the hot-path scope and raise
-    NotImplementedError.
+    NotImplementedError; fancy assignment raises like the reference.
 """
 import numbers
 import warnings
@@ -256,10 +256,59 @@ class FlatSparray(_BaseSparray):
         return FlatSparray(new_idx, new_val, tuple(new_shape), is_canonical=True)
 
     def __setitem__(self, indices, val):                                  # flat.py:327-364
-        raise NotImplementedError("assignment is outside the hot-path scope of sparray_b200 (SURVEY.md 8f)")
+        items, kind = ix.prepare_indices(indices, self.shape)
+        if kind == ix.EMPTY_SLICE_INDEX_MASK:
+            raise ValueError("Assigning to entire FlatSparray would densify.")
+        dev = self.indices.device
+        if kind == ix.INTEGER_INDEX_MASK:
+            flat = int(np.ravel_multi_index(items, self.shape))
+            self._setitem_flatidx(torch.tensor([flat], dtype=torch.int64, device=dev), val)
+            return
+        if not (kind & ix.ARRAY_INDEX_MASK):                          # ints + slices: the whole box gets stored
+            ranges, idx_shape = ix.indices_to_ranges(items, self.shape)
+            if any(s == 0 for s in idx_shape):
+                return
+            if np.any(ranges[:, 2] < 0):
+                raise NotImplementedError("negative slice steps are not supported")
+            n = int(np.prod(idx_shape, dtype=object)) if idx_shape else 1
+            box = _k.combine_ranges(ranges, self.shape, n, inner=False, device=dev)
+            self._setitem_flatidx(box, val)
+            return
+        raise NotImplementedError("Fancy assignment is still NYI")
 
     def setdiag(self, values, offset=0):                                  # flat.py:139-160
-        raise NotImplementedError("setdiag is outside the hot-path scope of sparray_b200 (SURVEY.md 8f)")
+        if len(self.shape) < 2:
+            raise ValueError("setdiag() requires at least two dimensions")
+        if len(self.shape) > 2:
+            raise NotImplementedError("setdiag() is NYI for ndim > 2")
+        if offset >= 0:
+            n = min(self.shape[0], self.shape[1] - offset)
+            ranges = [[0, n, 1], [offset, n + offset, 1]]
+        else:
+            n = min(self.shape[0] + offset, self.shape[1])
+            ranges = [[-offset, n - offset, 1], [0, n, 1]]
+        if n <= 0:
+            return self
+        diag = _k.combine_ranges(ranges, self.shape, n, inner=True, device=self.indices.device)
+        self._setitem_flatidx(diag, values)
+
+    def _setitem_flatidx(self, flat_idx, values):                         # flat.py:395-407
+        """Store `values` (scalar or one per index) at sorted flat indices: one fused union merge
+        in which the assigned value wins and untouched elements survive; the structure grows as
+        needed.  Mutates this array like the reference does."""
+        n = flat_idx.numel()
+        if np.isscalar(values) or (hasattr(values, "ndim") and values.ndim == 0):
+            vals = torch.full((n,), values.item() if hasattr(values, "item") else values,
+                              dtype=self.data.dtype, device=flat_idx.device)
+        else:
+            vals = _to_device(values, self.data.dtype)
+            if vals.numel() == 1:
+                vals = vals.expand(n).contiguous()
+            if vals.numel() != n:
+                raise ValueError("shape mismatch: value array of size %d could not be broadcast to indexing "
+                                 "result of size %d" % (vals.numel(), n))
+        idx, data = _k.setop_binop("union", "override", self.indices, self.data, flat_idx, vals)
+        self.indices, self.data = idx, data
 
     # -- sparse (op) sparse helpers (flat.py:409-434) ---------------------------------------------
     def _promoted(self, other, op):

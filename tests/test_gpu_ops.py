@@ -255,3 +255,47 @@ def test_converters_and_unary(sp):
     assert sp.is_sparray(A) and not sp.is_sparray(D)
     with pytest.raises(NotImplementedError):
         A += A
+
+
+def test_assignment_and_setdiag(sp):
+    """__setitem__ / setdiag (flat.py:327-364,139-160,395-407); the reference's
+    own assertions (sparray/tests/test_indexing.py:99-145) against dense numpy / scipy."""
+    import scipy.sparse as ss
+    dense1d = np.arange(5) - 2
+    dense2d = np.array([[0, 0, 0], [4, 5, 7], [6, 2, 0], [1, 3, 8]], dtype=float) / 2.
+    sp1d = sp.FlatSparray([0, 1, 3, 4], [-2, -1, 1, 2], shape=dense1d.shape)
+    sp2d = sp.FlatSparray([1, 3, 4, 5, 6, 7, 9, 10, 11], [0, 2, 2.5, 3.5, 3, 1, 0.5, 1.5, 4], shape=dense2d.shape)
+    for index in [3, 2, slice(None, 3)]:                       # in structure, not in structure, sub-array
+        a, d = sp1d.copy(), dense1d.copy()
+        a[index] = 99
+        d[index] = 99
+        np.testing.assert_array_equal(d, a.toarray())
+    for index in [(3, 1), (0, 2), (slice(None, 2), slice(None, 2)), (slice(1, None), 2)]:
+        a, d = sp2d.copy(), dense2d.copy()
+        a[index] = 99
+        d[index] = 99
+        np.testing.assert_array_equal(d, a.toarray())
+        assert np.all(np.diff(a.indices.cpu().numpy()) > 0)
+    a, d = sp2d.copy(), dense2d.copy()
+    a[1:3, 0:2] = np.array([1., 2., 3., 4.])                   # one value per cell of the box
+    d[1:3, 0:2] = np.array([[1., 2.], [3., 4.]])
+    np.testing.assert_array_equal(d, a.toarray())
+    with pytest.raises(ValueError):
+        sp2d.copy()[:] = 1
+    with pytest.raises(NotImplementedError):
+        sp2d.copy()[[0, 1], 1] = 1
+    sparse2d = ss.csr_matrix(dense2d)
+    for k in [0, 1, -1, 2, -2]:
+        a, m = sp2d.copy(), sparse2d.copy().tolil()
+        a.setdiag(99, offset=k)
+        m.setdiag(99, k=k)
+        np.testing.assert_array_equal(m.toarray(), a.toarray(), err_msg="k=%d" % k)
+    # larger, random: assign a strided box into a 3-D array
+    rng = np.random.default_rng(22)
+    shape = (40, 30, 20)
+    idx, val = rand_operand(rng, shape, 5000, np.float32)
+    A = sp.FlatSparray(idx, val, shape=shape, is_canonical=True)
+    D = fo.toarray(idx, val, shape)
+    A[3:35:2, 5, 1:19:3] = -7.5
+    D[3:35:2, 5, 1:19:3] = -7.5
+    np.testing.assert_array_equal(D, A.toarray())
