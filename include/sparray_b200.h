@@ -41,7 +41,8 @@ enum spb_binop {
     SPB_LT = 5, SPB_LE = 6, SPB_GT = 7, SPB_GE = 8, SPB_EQ = 9, SPB_NE = 10,   /* -> bool output */
     SPB_TAKE_A = 11, SPB_TAKE_B = 12,
     SPB_OVERRIDE = 13,   /* union only: b where b is stored, else a -- _setitem_flatidx, flat.py:395-407 */
-    SPB_BINOP_COUNT = 14
+    SPB_DIVIDE = 14, SPB_FLOOR_DIVIDE = 15,   /* spb_binary_map only (dense operand, flat.py:444-449,534-536) */
+    SPB_BINOP_COUNT = 16
 };
 
 /* unary / scalar value maps: flat.py:580-581,677-739, compat.py:96-102 */
@@ -137,6 +138,11 @@ int spb_intersect_binop(int op, int dtype,
 int spb_unary_map(int op, int dtype, const void* in, void* out, int64_t n,
                   double scalar_f, int64_t scalar_i, spb_stream_t stream);
 
+/* out[i] = a[i] (op) b[i] on two aligned value arrays of dtype `dtype` (comparisons -> SPB_BOOL):
+ * the dense (op) sparse helpers _pairwise_dense2dense / _pairwise_dense2sparse (flat.py:436-449)
+ * once the dense operand has been gathered at the stored indices with spb_gather. */
+int spb_binary_map(int op, int dtype, const void* a, const void* b, void* out, int64_t n, spb_stream_t stream);
+
 /* astype (flat.py:713-714) */
 int spb_cast(int dtype_in, int dtype_out, const void* in, void* out, int64_t n, spb_stream_t stream);
 
@@ -230,6 +236,16 @@ int spb_outer_sum(const int64_t* offsets, int ndim, const int64_t* lens_host, in
 int spb_lookup_compact(int dtype, const int64_t* sorted, const void* val, int64_t n,
                        const int64_t* query, int64_t nq, int64_t* out_idx, void* out_val,
                        int64_t* out_count, spb_workspace* ws, spb_stream_t stream);
+
+/* ---- 7. sparse broadcasting: flat.py:451-472 ------------------------------------ */
+
+/* Replicates every stored element along the axes where in_shape is 1 and out_shape is larger
+ * (both HOST int64[ndim], in_shape already left-padded with ones): out_idx/out_val get
+ * n * prod(broadcast dims) pairs with flat indices in out_shape, NOT sorted (follow with
+ * spb_rekey_sort).  The reference densifies here (flat.py:470-472, "TODO: fix this hack"). */
+int spb_broadcast_expand(int dtype, const int64_t* idx, const void* val, int64_t n, int ndim,
+                         const int64_t* in_shape_host, const int64_t* out_shape_host,
+                         int64_t* out_idx, void* out_val, spb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,8 @@ _NP_TO_TORCH = {np.dtype(v): k for k, v in _TORCH_TO_NP.items()}
 
 # enum spb_binop
 BINOPS = {"add": 0, "sub": 1, "mul": 2, "minimum": 3, "maximum": 4,
-          "lt": 5, "le": 6, "gt": 7, "ge": 8, "eq": 9, "ne": 10, "take_a": 11, "take_b": 12, "override": 13}
+          "lt": 5, "le": 6, "gt": 7, "ge": 8, "eq": 9, "ne": 10, "take_a": 11, "take_b": 12, "override": 13,
+          "divide": 14, "floor_divide": 15}
 COMPARISONS = ("lt", "le", "gt", "ge", "eq", "ne")
 
 # enum spb_unop (same order as the header)

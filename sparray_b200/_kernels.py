@@ -151,6 +151,13 @@ def scatter_dense(idx, val, size):
     return dense
 
 
+def scatter_into(dense, idx, val):
+    """dense[idx[i]] = val[i] in place (dense is a flat device tensor of val's dtype)."""
+    require_cuda()
+    check(lib.spb_scatter_dense(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), idx.numel(), ptr(dense), stream()))
+    return dense
+
+
 def gather(src, pos):
     require_cuda()
     out = torch.empty(pos.numel(), dtype=src.dtype, device=src.device)
@@ -343,3 +350,29 @@ def lookup_compact(sorted_idx, val, query):
                                  nq, ptr(out_idx), ptr(out_val), ptr(cnt), workspace(), stream()))
     k = _count(cnt)
     return out_idx[:k].clone(), out_val[:k].clone()
+
+
+# ---- section 7: sparse broadcasting, dense operands ---------------------------------------------------
+
+def binary_map(op, a, b):
+    """Elementwise a (op) b on two aligned device vectors of one dtype."""
+    require_cuda()
+    assert a.dtype == b.dtype and a.numel() == b.numel()
+    out = torch.empty_like(a, dtype=torch.bool if op in dt.COMPARISONS else a.dtype)
+    check(lib.spb_binary_map(dt.BINOPS[op], dt.spb_dtype(a.dtype), ptr(a), ptr(b), ptr(out), a.numel(), stream()))
+    return out
+
+
+def broadcast_expand(idx, val, in_shape, out_shape):
+    """Unsorted (index, value) pairs of the array broadcast from in_shape (left-padded) to out_shape."""
+    require_cuda()
+    ins = np.ascontiguousarray(in_shape, dtype=np.int64)
+    outs = np.ascontiguousarray(out_shape, dtype=np.int64)
+    reps = int(np.prod([o for i, o in zip(ins, outs) if i == 1 and o > 1], dtype=object))
+    n_out = idx.numel() * reps
+    out_idx = torch.empty(n_out, dtype=torch.int64, device=idx.device)
+    out_val = torch.empty(n_out, dtype=val.dtype, device=idx.device)
+    check(lib.spb_broadcast_expand(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), idx.numel(), len(ins),
+                                   ins.ctypes.data_as(ctypes.c_void_p), outs.ctypes.data_as(ctypes.c_void_p),
+                                   ptr(out_idx), ptr(out_val), stream()))
+    return out_idx, out_val

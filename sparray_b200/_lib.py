@@ -58,6 +58,8 @@ PROTOTYPES = {
     "spb_intersect_binop": (c_int, [c_int, c_int, c_p, c_p, c_i64, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p]),
     "spb_unary_map": (c_int, [c_int, c_int, c_p, c_p, c_i64, c_f64, c_i64, c_p]),
     "spb_cast": (c_int, [c_int, c_int, c_p, c_p, c_i64, c_p]),
+    "spb_binary_map": (c_int, [c_int, c_int, c_p, c_p, c_p, c_i64, c_p]),
+    "spb_broadcast_expand": (c_int, [c_int, c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p, c_p]),
     "spb_scatter_dense": (c_int, [c_int, c_p, c_p, c_i64, c_p, c_p]),
     "spb_gather": (c_int, [c_int, c_p, c_p, c_i64, c_p, c_p]),
     "spb_lower_bound": (c_int, [c_p, c_i64, c_p, c_i64, c_p, c_p, c_p]),

@@ -229,3 +229,91 @@ int spb_lookup_compact(int dtype, const int64_t* sorted, const void* val, int64_
 }
 
 }  // extern "C"
+
+// ---- sparse broadcasting without densifying (flat.py:451-472; the reference densifies there) --------
+namespace spb {
+
+struct ExpandParams {
+    int ndim;                          // merged axes of the (left-padded) input shape
+    FastDiv in_div[kBoxDims];          // C-order stride of the axis in the input shape
+    int64_t out_mul[kBoxDims];         // stride of the axis in the output shape (0 for size-1 / broadcast axes)
+    int nb;                            // broadcast axes
+    FastDiv b_div[kBoxDims];           // C-order stride of broadcast axis j inside the replica box
+    int64_t b_mul[kBoxDims];           // its stride in the output shape
+    FastDiv reps;                      // replicas per stored element
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) broadcast_expand_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
+                                                               int64_t n_out, const ExpandParams e,
+                                                               int64_t* __restrict__ out_idx, T* __restrict__ out_val) {
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n_out; o += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = fastdiv((uint64_t)o, e.reps);
+        uint64_t c = (uint64_t)o - i * e.reps.d;
+        uint64_t rem = (uint64_t)idx[i];
+        int64_t key = 0;
+        for (int ax = 0; ax < e.ndim; ++ax) {
+            const uint64_t q = fastdiv(rem, e.in_div[ax]);
+            rem -= q * e.in_div[ax].d;
+            key += (int64_t)q * e.out_mul[ax];
+        }
+        for (int j = 0; j < e.nb; ++j) {
+            const uint64_t q = fastdiv(c, e.b_div[j]);
+            c -= q * e.b_div[j].d;
+            key += (int64_t)q * e.b_mul[j];
+        }
+        out_idx[o] = key;
+        out_val[o] = val[i];
+    }
+}
+
+}  // namespace spb
+
+extern "C" int spb_broadcast_expand(int dtype, const int64_t* idx, const void* val, int64_t n, int ndim,
+                                    const int64_t* in_shape, const int64_t* out_shape, int64_t* out_idx, void* out_val,
+                                    spb_stream_t stream) {
+    using namespace spb;
+    if (n < 0 || ndim < 1 || ndim > kBoxDims || !in_shape || !out_shape) return SPB_ERR_BAD_ARG;
+    ExpandParams e{};
+    e.ndim = ndim;
+    int64_t in_stride = 1, out_stride = 1, reps = 1;
+    int64_t bdim[kBoxDims], bmul[kBoxDims];
+    int nb = 0;
+    for (int ax = ndim - 1; ax >= 0; --ax) {
+        if (in_shape[ax] != out_shape[ax] && in_shape[ax] != 1) return SPB_ERR_BAD_ARG;
+        e.in_div[ax] = make_fastdiv((uint64_t)in_stride);
+        e.out_mul[ax] = in_shape[ax] == 1 ? 0 : out_stride;
+        if (in_shape[ax] == 1 && out_shape[ax] > 1) {
+            bdim[nb] = out_shape[ax];
+            bmul[nb] = out_stride;
+            ++nb;
+        }
+        in_stride *= in_shape[ax];
+        out_stride *= out_shape[ax];
+    }
+    // broadcast axes were collected innermost first: store them outermost first with C-order strides
+    e.nb = nb;
+    for (int j = 0; j < nb; ++j) {
+        const int src = nb - 1 - j;
+        e.b_mul[j] = bmul[src];
+    }
+    int64_t s = 1;
+    for (int j = nb - 1; j >= 0; --j) {
+        e.b_div[j] = make_fastdiv((uint64_t)s);
+        s *= bdim[nb - 1 - j];
+    }
+    reps = s;
+    e.reps = make_fastdiv((uint64_t)reps);
+    const int64_t n_out = n * reps;
+    if (n_out == 0) return SPB_OK;
+    if (!idx || !val || !out_idx || !out_val) return SPB_ERR_BAD_ARG;
+    int64_t blocks = ceil_div(n_out, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+#define SPB_EXP(T)                                                                                              \
+    broadcast_expand_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(idx, (const T*)val, n_out, e, out_idx,    \
+                                                                     (T*)out_val);                              \
+    SPB_LAUNCHED(1);                                                                                            \
+    return (int)cudaGetLastError()
+    SPB_BY_SIZE(dtype, SPB_EXP)
+#undef SPB_EXP
+}

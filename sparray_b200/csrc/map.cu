@@ -174,6 +174,51 @@ __global__ void __launch_bounds__(kMapThreads) unary_kernel(const T* __restrict_
     }
 }
 
+// out[i] = a[i] (op) b[i] on two aligned value arrays: the dense (op) sparse helpers of
+// flat.py:436-449 after the dense operand has been gathered at the stored indices
+template <typename T, typename TO, bool CMP>
+__global__ void __launch_bounds__(kMapThreads) binary_kernel(const T* __restrict__ a, const T* __restrict__ b,
+                                                             TO* __restrict__ out, int64_t n, int op) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const T x = a[i], y = b[i];
+        if constexpr (CMP) {
+            uint8_t r;
+            switch (op) {
+                case SPB_LT: r = x < y; break;
+                case SPB_LE: r = x <= y; break;
+                case SPB_GT: r = x > y; break;
+                case SPB_GE: r = x >= y; break;
+                case SPB_EQ: r = x == y; break;
+                default: r = x != y; break;
+            }
+            out[i] = (TO)r;
+        } else {
+            T r;
+            switch (op) {
+                case SPB_ADD: r = x + y; break;
+                case SPB_SUB: r = x - y; break;
+                case SPB_MUL: r = x * y; break;
+                case SPB_MINIMUM:
+                    if constexpr (T(0.5) != T(0)) r = x != x ? x : (x < y ? x : y);
+                    else r = x < y ? x : y;
+                    break;
+                case SPB_MAXIMUM:
+                    if constexpr (T(0.5) != T(0)) r = x != x ? x : (x > y ? x : y);
+                    else r = x > y ? x : y;
+                    break;
+                case SPB_DIVIDE:
+                    if constexpr (T(0.5) != T(0)) r = x / y;
+                    else r = floor_div<T>(x, y);
+                    break;
+                case SPB_FLOOR_DIVIDE: r = floor_div<T>(x, y); break;
+                case SPB_TAKE_A: r = x; break;
+                default: r = y; break;
+            }
+            out[i] = (TO)r;
+        }
+    }
+}
+
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(kMapThreads) cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n,
                                                            int to_bool) {
@@ -363,6 +408,28 @@ int spb_unary_map(int op, int dtype, const void* in, void* out, int64_t n, doubl
         default: return SPB_ERR_UNSUPPORTED;
     }
 #undef SPB_UNARY
+}
+
+int spb_binary_map(int op, int dtype, const void* a, const void* b, void* out, int64_t n, spb_stream_t stream) {
+    if (n < 0) return SPB_ERR_BAD_ARG;
+    if (n == 0) return SPB_OK;
+    if (!a || !b || !out) return SPB_ERR_BAD_ARG;
+    const bool cmp = op >= SPB_LT && op <= SPB_NE;
+    const unsigned grid = grid_for(n, kMapThreads * 4);
+#define SPB_BIN(T)                                                                                          \
+    if (cmp) binary_kernel<T, uint8_t, true><<<grid, kMapThreads, 0, stream>>>((const T*)a, (const T*)b,    \
+                                                                               (uint8_t*)out, n, op);       \
+    else binary_kernel<T, T, false><<<grid, kMapThreads, 0, stream>>>((const T*)a, (const T*)b, (T*)out, n, op); \
+    SPB_LAUNCHED(1);                                                                                         \
+    return (int)cudaGetLastError()
+    switch (dtype) {
+        case SPB_F32: SPB_BIN(float);
+        case SPB_F64: SPB_BIN(double);
+        case SPB_I32: SPB_BIN(int32_t);
+        case SPB_I64: SPB_BIN(int64_t);
+        default: return SPB_ERR_UNSUPPORTED;
+    }
+#undef SPB_BIN
 }
 
 int spb_cast(int dtype_in, int dtype_out, const void* in, void* out, int64_t n, spb_stream_t stream) {

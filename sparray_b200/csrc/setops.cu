@@ -785,7 +785,8 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
 
 template <int KIND>
 int dispatch_binop(int op, int dtype, SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
-    if (op < 0 || op >= SPB_BINOP_COUNT) return SPB_ERR_BAD_ARG;
+    if (op < 0 || op > SPB_OVERRIDE) return SPB_ERR_BAD_ARG;        // divide ops exist for spb_binary_map only
+    if (op == SPB_OVERRIDE && KIND != KIND_UNION) return SPB_ERR_BAD_ARG;
     const bool cmp = op >= SPB_LT && op <= SPB_NE;
     p.op = op == SPB_SUB ? SPB_ADD : op;
     p.negate_b = op == SPB_SUB;

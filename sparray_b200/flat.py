@@ -14,9 +14,11 @@ Deliberate divergences from the reference:
   * ``dot`` with a dense vector is an O(nnz) SpMV (flat.py:568 densifies, F7);
   * ``__getitem__`` returns sorted (canonical) results for unsorted fancy
     queries and numpy semantics for repeated ones;
-  * branches that densify (sparse + nonzero scalar, sparse / sparse, ...) and
-    mixed dense-ndarray operands are out of the hot-path scope and raise
-    NotImplementedError; fancy assignment raises like the reference.
+  * broadcasting between sparse operands stays sparse (index-expansion kernel + sort)
+    instead of densifying (flat.py:470-472);
+  * branches whose RESULT is dense by nature in the reference and that involve no dense
+    operand (sparse + nonzero scalar, sparse / sparse, sparse ** 0, ...) are out of the
+    hot-path scope and raise NotImplementedError; fancy assignment raises like the reference.
 """
 import numbers
 import warnings
@@ -336,16 +338,83 @@ class FlatSparray(_BaseSparray):
         idx, val = _k.setop_binop("intersect", op, self.indices, a_val, other.indices, b_val)
         return FlatSparray(idx, val, self.shape, is_canonical=True)
 
-    def _check_operand(self, other, what):
+    # -- broadcasting and dense operands (flat.py:436-472) ------------------------------------------
+    def _broadcast(self, shape):
+        """This array broadcast to `shape`, WITHOUT densifying (the reference densifies here,
+        flat.py:470-472 "TODO: fix this hack"): an index-expansion kernel replicates the stored
+        elements along the broadcast axes, then one radix sort makes the result canonical.  Like
+        the reference's dense detour (from_ndarray), explicit zeros do not survive."""
+        shape = tuple(int(s) for s in shape)
+        padded = (1,) * (len(shape) - len(self.shape)) + tuple(self.shape)
+        for i, o in zip(padded, shape):
+            if i != o and i != 1:
+                raise ValueError("shape mismatch: objects cannot be broadcast to a single shape")
+        idx, val = _k.broadcast_expand(self.indices, self.data, padded, shape)
+        bits = max(int(np.prod(shape, dtype=object)) - 1, 1).bit_length()
+        idx, val = _k.rekey_sort(idx, val, [], [], 1, bits)
+        keep = _k.unary_map("ne_s", val, 0)
+        idx, val = _k.select_pairs(idx, val, keep)
+        return FlatSparray(idx, val, shape, is_canonical=True)
+
+    def _handle_broadcasting(self, other):
+        """(lhs, rhs) with a common shape; rhs is a FlatSparray or a C-contiguous device tensor."""
         if ss is not None and ss.issparse(other):
             other = FlatSparray.from_spmatrix(other)
-        if not isinstance(other, FlatSparray):
-            raise NotImplementedError("FlatSparray %s dense operand densifies or leaves the sorted-index path; "
-                                      "out of sparray_b200's scope" % what)
-        if other.shape != self.shape:
-            raise NotImplementedError("broadcasting densifies in the reference (flat.py:470-472); "
-                                      "out of sparray_b200's scope")
-        return other
+        if isinstance(other, FlatSparray):
+            if other.shape == self.shape:
+                return self, other
+            bshape = tuple(int(s) for s in np.broadcast_shapes(self.shape, other.shape))
+            lhs = self if self.shape == bshape else self._broadcast(bshape)
+            rhs = other if other.shape == bshape else other._broadcast(bshape)
+            return lhs, rhs
+        if isinstance(other, torch.Tensor):
+            dense = other.to(self.indices.device)
+            oshape = tuple(dense.shape)
+        else:
+            arr = np.asarray(other)
+            dt.torch_dtype(arr.dtype)
+            oshape = arr.shape
+            dense = None
+        bshape = tuple(int(s) for s in np.broadcast_shapes(self.shape, oshape))
+        lhs = self if self.shape == bshape else self._broadcast(bshape)
+        if dense is None:
+            dense = torch.from_numpy(np.array(np.broadcast_to(arr, bshape), order="C")).to(self.indices.device)
+        else:
+            dense = dense.expand(bshape).contiguous()
+        return lhs, dense
+
+    def _pairwise_dense2dense(self, other, op):
+        """op(dense, sparse) -> dense ndarray with the dense operand's dtype (flat.py:436-442):
+        gather the touched cells, combine, scatter back into a copy."""
+        flat = other.reshape(-1)
+        cells = _k.gather(flat, self.indices)
+        common = dt.promote(cells.dtype, self.data.dtype)
+        a = cells if cells.dtype == common else _k.cast(cells, common)
+        b = self.data if self.data.dtype == common else _k.cast(self.data, common)
+        r = _k.binary_map(op, a, b)
+        if r.dtype != flat.dtype:
+            r = _k.cast(r, flat.dtype)
+        out = flat.clone()
+        _k.scatter_into(out, self.indices, r)
+        return out.reshape(other.shape).cpu().numpy()
+
+    def _pairwise_dense2sparse(self, other, op):
+        """op(sparse, dense) -> sparse on this array's structure (flat.py:444-449)."""
+        cells = _k.gather(other.reshape(-1), self.indices)
+        common = dt.promote(cells.dtype, self.data.dtype)
+        a = self.data if self.data.dtype == common else _k.cast(self.data, common)
+        b = cells if cells.dtype == common else _k.cast(cells, common)
+        return self._with_data(_k.binary_map(op, a, b))
+
+    def _dense_elementwise(self, other, op):
+        """op(self.toarray(), dense) computed on the device -> dense ndarray (the reference's
+        `ufunc(self.toarray(), other)` branches, e.g. flat.py:488,593,605)."""
+        mine = self.todense_device().reshape(-1)
+        flat = other.reshape(-1)
+        common = dt.promote(mine.dtype, flat.dtype)
+        a = mine if mine.dtype == common else _k.cast(mine, common)
+        b = flat if flat.dtype == common else _k.cast(flat, common)
+        return _k.binary_map(op, a, b).reshape(other.shape).cpu().numpy()
 
     def _comparison(self, other, method_name, op, op_symbol):              # flat.py:474-488
         if _is_scalar(other):
@@ -356,8 +425,10 @@ class FlatSparray(_BaseSparray):
             kind = "nonzero scalar" if other != 0 else "0"
             warnings.warn("FlatSparray %s %s densifies" % (op_symbol, kind), _EfficiencyWarning)
             raise NotImplementedError("densifying comparison is out of sparray_b200's scope")
-        other = self._check_operand(other, op_symbol)
-        return self._pairwise_sparray(other, op)
+        lhs, rhs = self._handle_broadcasting(other)
+        if isinstance(rhs, FlatSparray):
+            return lhs._pairwise_sparray(rhs, op)
+        return lhs._dense_elementwise(rhs, op)
 
     def __add__(self, other):                                              # flat.py:490-505
         if _is_scalar(other):
@@ -365,25 +436,44 @@ class FlatSparray(_BaseSparray):
                 return self.copy()
             warnings.warn("FlatSparray + nonzero scalar densifies", _EfficiencyWarning)
             raise NotImplementedError("densifying add is out of sparray_b200's scope")
-        return self._pairwise_sparray(self._check_operand(other, "+"), "add")
+        lhs, rhs = self._handle_broadcasting(other)
+        if isinstance(rhs, FlatSparray):
+            return lhs._pairwise_sparray(rhs, "add")
+        return lhs._pairwise_dense2dense(rhs, "add")
 
     def __sub__(self, other):                                              # base.py:45-46
         # a - b == a + (-b) bit for bit (IEEE / two's complement); fused so -b is never materialised
         if _is_scalar(other):
             return self.__add__(-other)
-        return self._pairwise_sparray(self._check_operand(other, "-"), "sub")
+        lhs, rhs = self._handle_broadcasting(other)
+        if isinstance(rhs, FlatSparray):
+            return lhs._pairwise_sparray(rhs, "sub")
+        # dense: a + (-b) with the dense operand negated on the device
+        neg = _k.unary_map("neg", rhs.reshape(-1)).reshape(rhs.shape)
+        return lhs._pairwise_dense2dense(neg, "add")
 
     def __mul__(self, other):                                              # flat.py:507-518
         if _is_scalar(other):
             return self._scalar_map("mul_s", other)
-        return self._pairwise_sparray_fixed_zero(self._check_operand(other, "*"), "mul")
+        lhs, rhs = self._handle_broadcasting(other)
+        if isinstance(rhs, FlatSparray):
+            return lhs._pairwise_sparray_fixed_zero(rhs, "mul")
+        return lhs._pairwise_dense2sparse(rhs, "mul")
 
     def _divide(self, other, div_func="divide", rdivide=False):            # flat.py:520-536
-        if rdivide or not _is_scalar(other):
+        if (ss is not None and ss.issparse(other)) or isinstance(other, FlatSparray) or rdivide:
             raise NotImplementedError("this division densifies in the reference (flat.py:522-527); out of scope")
-        if div_func == "true_divide" or (div_func == "divide"):
-            return self.__mul__(1. / other)                                # flat.py:528-529
-        return self._scalar_map("floordiv_s", other)
+        if _is_scalar(other):
+            if div_func in ("true_divide", "divide"):
+                return self.__mul__(1. / other)                            # flat.py:528-529
+            return self._scalar_map("floordiv_s", other)
+        lhs, rhs = self._handle_broadcasting(other)                        # dense / -> sparse on our structure
+        if div_func == "true_divide":
+            if not rhs.dtype.is_floating_point:
+                rhs = _k.cast(rhs.reshape(-1), torch.float64).reshape(rhs.shape)
+            if not lhs.data.dtype.is_floating_point:
+                lhs = lhs.astype(np.float64)
+        return lhs._pairwise_dense2sparse(rhs, "floor_divide" if div_func == "floor_divide" else "divide")
 
     def dot(self, other):                                                  # flat.py:538-568
         ax1 = len(self.shape) - 1
@@ -452,14 +542,20 @@ class FlatSparray(_BaseSparray):
             return self._scalar_map("min_s", other)
         if _is_scalar(other):
             raise NotImplementedError("minimum with a negative scalar densifies; out of scope")
-        return self._pairwise_sparray(self._check_operand(other, "minimum"), "minimum")
+        lhs, rhs = self._handle_broadcasting(other)
+        if isinstance(rhs, FlatSparray):
+            return lhs._pairwise_sparray(rhs, "minimum")
+        return lhs._dense_elementwise(rhs, "minimum")
 
     def maximum(self, other):                                              # flat.py:595-605
         if _is_scalar(other) and other <= 0:
             return self._scalar_map("max_s", other)
         if _is_scalar(other):
             raise NotImplementedError("maximum with a positive scalar densifies; out of scope")
-        return self._pairwise_sparray(self._check_operand(other, "maximum"), "maximum")
+        lhs, rhs = self._handle_broadcasting(other)
+        if isinstance(rhs, FlatSparray):
+            return lhs._pairwise_sparray(rhs, "maximum")
+        return lhs._dense_elementwise(rhs, "maximum")
 
     # -- reductions (flat.py:607-626) --------------------------------------------------------------
     def sum(self, axis=None, dtype=None):

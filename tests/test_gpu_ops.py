@@ -299,3 +299,52 @@ def test_assignment_and_setdiag(sp):
     A[3:35:2, 5, 1:19:3] = -7.5
     D[3:35:2, 5, 1:19:3] = -7.5
     np.testing.assert_array_equal(D, A.toarray())
+
+
+def test_dense_operands_and_sparse_broadcasting(sp):
+    """broadcasting between sparse operands without densifying and the
+    dense (op) sparse helpers (flat.py:436-472).  Mirrors the reference's assertions in
+    sparray/tests/test_math.py:26-47,57-64,66-94,224-228 against dense numpy."""
+    import scipy.sparse as ss
+    from numpy.testing import assert_array_equal
+    rng = np.random.default_rng(31)
+    dense2d = np.array([[0, 0, 0], [4, 5, 7], [6, 2, 0], [1, 3, 8]], dtype=float) / 2.
+    sp2d = sp.FlatSparray([1, 3, 4, 5, 6, 7, 9, 10, 11], [0, 2, 2.5, 3.5, 3, 1, 0.5, 1.5, 4], shape=dense2d.shape)
+    # dense ndarray operands, same shape and broadcast
+    for bshape in [dense2d.shape, (dense2d.shape[0], 1), (1, dense2d.shape[1])]:
+        b = rng.random(bshape)
+        assert_array_equal(dense2d + b, sp2d + b)
+        assert_array_equal(b + dense2d, b + sp2d)
+        assert_array_equal(dense2d - b, sp2d - b)
+        assert_array_equal(b - dense2d, b - sp2d)
+        assert_array_equal(dense2d * b, (sp2d * b).toarray())
+        assert_array_equal(b * dense2d, (b * sp2d).toarray())
+        assert_array_equal(dense2d < b, sp2d < b)
+        assert_array_equal(np.minimum(dense2d, b), sp2d.minimum(b))
+        assert_array_equal(np.maximum(dense2d, b), sp2d.maximum(b))
+        np.testing.assert_allclose((sp2d / (b + 1)).toarray(), dense2d / (b + 1), rtol=1e-15)
+        assert_array_equal((sp2d // (b + 1)).toarray(), dense2d // (b + 1))
+    # sparse operands that broadcast: (4,1) and (1,3) against (4,3)
+    for shape in [(dense2d.shape[0], 1), (1, dense2d.shape[1])]:
+        s = ss.random(*shape, density=0.6, random_state=5)
+        b = sp.FlatSparray.from_spmatrix(s)
+        sd = s.toarray()
+        r = sp2d + b
+        assert isinstance(r, sp.FlatSparray) and r.shape == dense2d.shape
+        assert_array_equal(dense2d + sd, r.toarray())
+        assert_array_equal(sd + dense2d, (b + sp2d).toarray())
+        assert_array_equal(dense2d * sd, (sp2d * b).toarray())
+        assert_array_equal(dense2d * sd, (b * sp2d).toarray())
+        assert_array_equal(np.maximum(dense2d, sd), sp2d.maximum(b).toarray())
+        assert np.all(np.diff(r.indices.cpu().numpy()) > 0)
+    # a bigger N-D broadcast: (6,1,8,1) with (6,5,8,7)
+    big = rng.standard_normal((6, 5, 8, 7)); big[rng.random(big.shape) < 0.7] = 0
+    small = rng.standard_normal((6, 1, 8, 1)); small[rng.random(small.shape) < 0.5] = 0
+    A, S = sp.FlatSparray.from_ndarray(big), sp.FlatSparray.from_ndarray(small)
+    assert_array_equal(big + small, (A + S).toarray())
+    assert_array_equal(big * small, (A * S).toarray())
+    assert_array_equal(small - big, (S - A).toarray())
+    low = sp.FlatSparray.from_ndarray(small[0, 0])             # fewer dims: (8,1) against 4-D
+    assert_array_equal(big + small[0, 0], (A + low).toarray())
+    wi, wv, _ = fo.from_ndarray(np.broadcast_to(small, big.shape))
+    assert_sparse_same(S._broadcast(big.shape), (wi, wv, big.shape))
