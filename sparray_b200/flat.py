@@ -67,6 +67,15 @@ def _to_device(x, dtype=None):
     return t.contiguous().reshape(-1)
 
 
+def _to_device_nd(x):
+    """numpy / torch array of any rank -> contiguous tensor on the current CUDA device."""
+    if isinstance(x, torch.Tensor):
+        return x.to(_device()).contiguous()
+    arr = np.asarray(x)
+    dt.torch_dtype(arr.dtype)
+    return torch.from_numpy(np.ascontiguousarray(arr)).to(_device())
+
+
 def _is_scalar(x):
     return np.isscalar(x) or (isinstance(x, (np.ndarray, torch.Tensor)) and x.ndim == 0)
 
@@ -481,9 +490,23 @@ class FlatSparray(_BaseSparray):
         ax2 = max(0, len(oshape) - 2)
         if self.shape[ax1] != oshape[ax2]:
             raise ValueError("shapes %s and %s not aligned" % (self.shape, oshape))
-        if len(oshape) != 1:
-            raise NotImplementedError("dot with a matrix operand (SpMM / SpGEMM) is out of scope (SURVEY.md 8f-4)")
         nrows = self._size() // self.shape[ax1] if self.shape[ax1] else 0
+        if len(oshape) == 2:
+            # matrix operand: one SpMV per column (dense result, like flat.py:568 without densifying self);
+            # a sparse matrix operand is densified column-wise the same way (the reference goes through scipy)
+            dense = other.todense_device() if isinstance(other, FlatSparray) else _to_device_nd(other)
+            cols = dense.t().contiguous()
+            vdt = dt.promote(self.data.dtype, cols.dtype)
+            out = torch.empty((oshape[1], nrows), dtype=vdt if vdt.is_floating_point else torch.float64,
+                              device=self.indices.device)
+            for j in range(oshape[1]):
+                out[j] = _k.spmv(self.indices, self.data, self.shape[ax1], nrows, cols[j], vdt)
+            res = out.t().contiguous().reshape(self.shape[:-1] + (oshape[1],))
+            if isinstance(other, FlatSparray):
+                return FlatSparray.from_ndarray(res)
+            return res.cpu().numpy()
+        if len(oshape) != 1:
+            raise NotImplementedError("dot with an operand of more than two dimensions is out of scope")
         if isinstance(other, FlatSparray):                                 # sparse vector: sparse result
             x = other.todense_device().reshape(-1)
             vdt = dt.promote(self.data.dtype, x.dtype)

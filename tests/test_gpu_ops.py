@@ -348,3 +348,22 @@ def test_dense_operands_and_sparse_broadcasting(sp):
     assert_array_equal(big + small[0, 0], (A + low).toarray())
     wi, wv, _ = fo.from_ndarray(np.broadcast_to(small, big.shape))
     assert_sparse_same(S._broadcast(big.shape), (wi, wv, big.shape))
+
+
+def test_dot_matrix_operands(sp):
+    """a.dot(B) for a dense or sparse 2-D B: one SpMV per column (flat.py:538-568; the reference's
+    assertions test_math.py:180-213, _matmul.py:19-28 against numpy)."""
+    rng = np.random.default_rng(33)
+    D = rng.standard_normal((30, 20)); D[rng.random(D.shape) < 0.7] = 0
+    Bm = rng.standard_normal((20, 7))
+    A = sp.FlatSparray.from_ndarray(D)
+    np.testing.assert_allclose(A.dot(Bm), D.dot(Bm), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(A @ Bm, D @ Bm, rtol=1e-12, atol=1e-12)
+    Bs = Bm.copy(); Bs[rng.random(Bs.shape) < 0.6] = 0
+    r = A.dot(sp.FlatSparray.from_ndarray(Bs))
+    assert isinstance(r, sp.FlatSparray) and r.shape == (30, 7)
+    np.testing.assert_allclose(r.toarray(), D.dot(Bs), rtol=1e-12, atol=1e-12)
+    T = rng.standard_normal((4, 5, 20)); T[rng.random(T.shape) < 0.5] = 0
+    np.testing.assert_allclose(sp.FlatSparray.from_ndarray(T).dot(Bm), T.dot(Bm), rtol=1e-12, atol=1e-12)
+    with pytest.raises(ValueError):
+        A.dot(np.ones((19, 3)))
