@@ -214,6 +214,17 @@ int spb_rekey_sort(int dtype, const int64_t* idx, const void* val, int64_t n,
                    int64_t* out_idx, void* out_val, int64_t* tmp_idx, void* tmp_val,
                    spb_workspace* ws, spb_stream_t stream);
 
+/* sum(axis != last) when prod(new_shape) (= cells) is small enough to hold densely: no sort.
+ * Every element adds into acc[new_key] (float64 atomics; acc: cells doubles, touched: cells bytes,
+ * 16-byte aligned, both zeroed here), then the touched cells are emitted in key order (explicit
+ * zeros survive).  Strides as in spb_rekey_sort.  out_idx / out_sums: min(n, cells) slots.  The
+ * order of the additions is not fixed, so sums may differ in the last bits from run to run. */
+int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val, int64_t n,
+                       int ndim, const int64_t* in_strides_host, const int64_t* out_strides_host,
+                       int64_t cells, double* acc, uint8_t* touched,
+                       int64_t* out_idx, double* out_sums, int64_t* out_count,
+                       spb_workspace* ws, spb_stream_t stream);
+
 /* ---- 6. __getitem__: flat.py:254-325, 366-393 ---------------------------------- */
 
 /* ints + slices (flat.py:270-274) without materialising the box: keeps the stored

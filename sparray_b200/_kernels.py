@@ -275,15 +275,43 @@ def transpose(idx, val, shape, axes):
     return rekey_sort(idx, val, in_s, out_s, div, bits)
 
 
+DENSE_SUM_MAX_CELLS = 1 << 26      # 512 MiB of float64 accumulators
+
+
 def sum_axis(idx, val, shape, axis):
-    """(new sorted unique flat indices, float64 sums) -- flat.py:617-625."""
+    """(new sorted unique flat indices, float64 sums) -- flat.py:617-625.
+    last axis: segmented reduce, no sort; otherwise a dense float64 accumulator when the reduced
+    array is small enough to hold (no sort either), else re-key + radix sort + segmented reduce."""
     from . import _plan
     plan = _plan.axis_sum_plan(shape, axis)
     if plan[0] == "last":
         return reduce_by_key(idx, val, plan[1])
     _, in_s, out_s, bits = plan
+    n = idx.numel()
+    cells = _plan.prod(shape) // int(shape[axis])
+    if n and cells <= DENSE_SUM_MAX_CELLS and cells <= 64 * n + (1 << 22):
+        return axis_sum_dense(idx, val, in_s, out_s, cells)
     keys, vals = rekey_sort(idx, val, in_s, out_s, 1, bits)
     return reduce_by_key(keys, vals, 1)
+
+
+def axis_sum_dense(idx, val, in_strides, out_strides, cells):
+    require_cuda()
+    n = idx.numel()
+    cap = min(n, cells)
+    acc = torch.empty(cells, dtype=torch.float64, device=idx.device)
+    touched = torch.empty(cells, dtype=torch.uint8, device=idx.device)
+    out_idx = torch.empty(cap, dtype=torch.int64, device=idx.device)
+    out_sums = torch.empty(cap, dtype=torch.float64, device=idx.device)
+    cnt = torch.empty(1, dtype=torch.int64, device=idx.device)
+    ndim = len(in_strides)
+    ins = (ctypes.c_int64 * ndim)(*in_strides)
+    outs = (ctypes.c_int64 * ndim)(*out_strides)
+    check(lib.spb_axis_sum_dense(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), n, ndim,
+                                 ctypes.cast(ins, ctypes.c_void_p), ctypes.cast(outs, ctypes.c_void_p), int(cells),
+                                 ptr(acc), ptr(touched), ptr(out_idx), ptr(out_sums), ptr(cnt), workspace(), stream()))
+    k = _count(cnt)
+    return _trim(out_idx, k), _trim(out_sums, k)
 
 
 def canonicalize(idx, val, max_key=None):

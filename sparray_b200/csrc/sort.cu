@@ -384,3 +384,102 @@ int spb_rekey_sort(int dtype, const int64_t* idx, const void* val, int64_t n, in
 }
 
 }  // extern "C"
+
+// ---- axis sums into a dense accumulator (no sort) ---------------------------------------------------
+// When the reduced array prod(new_shape) is small enough to hold densely, sum(axis != last)
+// (flat.py:617-625) does not need the re-key + radix sort at all: every stored element adds its
+// value into acc[new_key] with a float64 atomic (the accumulator is L2-resident for the BASELINE
+// configs), marks the cell as touched (explicit zeros must survive, so "sum == 0" cannot be the
+// test), and one compaction pass over the cells emits the touched ones in key order.
+namespace spb {
+
+template <typename T>
+__global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
+                                                              int64_t n, const Rekey rk, double* __restrict__ acc,
+                                                              uint8_t* __restrict__ touched) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t key = apply_rekey(__ldcs(idx + i), rk);
+        atomicAdd(acc + key, (double)__ldcs(val + i));
+        touched[key] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) select_touched_kernel(const double* __restrict__ acc, const uint8_t* __restrict__ touched,
+                                                             int64_t cells, int64_t* __restrict__ out_idx,
+                                                             double* __restrict__ out_val, int64_t* out_count,
+                                                             uint64_t* state, uint32_t epoch) {
+    constexpr int VT = 16;
+    const int64_t tile = blockIdx.x;
+    const int64_t first = tile * (256 * VT) + (int64_t)threadIdx.x * VT;
+    unsigned bits = 0;
+    if (first + VT <= cells) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(touched + first);     // 16 flags at once (first % 16 == 0)
+        const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int k = 0; k < VT; ++k) bits |= (((w[k >> 2] >> (8 * (k & 3))) & 0xffu) ? 1u : 0u) << k;
+    } else {
+        for (int k = 0; k < VT; ++k)
+            if (first + k < cells && touched[first + k]) bits |= 1u << k;
+    }
+    int64_t off = compact_offset_256(__popc(bits), state, epoch, tile, tile == gridDim.x - 1, out_count);
+#pragma unroll
+    for (int k = 0; k < VT; ++k) {
+        if (bits & (1u << k)) {
+            out_idx[off] = first + k;
+            out_val[off] = acc[first + k];
+            ++off;
+        }
+    }
+}
+
+}  // namespace spb
+
+extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val, int64_t n, int ndim,
+                                  const int64_t* in_strides, const int64_t* out_strides, int64_t cells, double* acc,
+                                  uint8_t* touched, int64_t* out_idx, double* out_sums, int64_t* out_count,
+                                  spb_workspace* ws, spb_stream_t stream) {
+    using namespace spb;
+    if (n < 0 || cells < 0 || ndim < 1 || ndim > kMaxRekeyDims || !in_strides || !out_strides || !out_count)
+        return SPB_ERR_BAD_ARG;
+    if (n == 0 || cells == 0) return (int)cudaMemsetAsync(out_count, 0, 8, stream);
+    if (!idx || !val || !acc || !touched || !out_idx || !out_sums) return SPB_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(touched) & 15) != 0) return SPB_ERR_BAD_ARG;
+    Rekey rk{};
+    rk.ndim = ndim;
+    for (int ax = 0; ax < ndim; ++ax) {
+        if (in_strides[ax] < 1 || out_strides[ax] < 0) return SPB_ERR_BAD_ARG;
+        rk.in_div[ax] = make_fastdiv((uint64_t)in_strides[ax]);
+        rk.out_mul[ax] = out_strides[ax];
+    }
+    SPB_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)cells * sizeof(double), stream));
+    SPB_CUDA_TRY(cudaMemsetAsync(touched, 0, (size_t)cells, stream));
+    int64_t blocks = ceil_div(n, 256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+#define SPB_ACC(T)                                                                                            \
+    axis_accumulate_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(idx, (const T*)val, n, rk, acc, touched); \
+    break
+    switch (dtype) {
+        case SPB_F32: SPB_ACC(float);
+        case SPB_F64: SPB_ACC(double);
+        case SPB_I32: SPB_ACC(int32_t);
+        case SPB_I64: SPB_ACC(int64_t);
+        case SPB_U8: case SPB_BOOL: SPB_ACC(uint8_t);
+        case SPB_I8: SPB_ACC(int8_t);
+        case SPB_I16: SPB_ACC(int16_t);
+        default: return SPB_ERR_UNSUPPORTED;
+    }
+#undef SPB_ACC
+    SPB_LAUNCHED(1);
+    SPB_CUDA_TRY(cudaGetLastError());
+    const int64_t ntiles = ceil_div(cells, 256 * 16);
+    if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
+    int rc = workspace_reserve(ws, (size_t)ntiles * 8, stream);
+    if (rc) return rc;
+    uint32_t epoch;
+    rc = workspace_next_epoch(ws, stream, &epoch);
+    if (rc) return rc;
+    select_touched_kernel<<<(unsigned)ntiles, 256, 0, stream>>>(acc, touched, cells, out_idx, out_sums, out_count,
+                                                                ws_state(ws), epoch);
+    SPB_LAUNCHED(1);
+    return (int)cudaGetLastError();
+}
