@@ -603,7 +603,30 @@ setop_kernel(const SetopParams p) {
         epa = p.tmp_apos + slot;
         epb = p.tmp_bpos + slot;
     }
-    if (KIND == KIND_UNION || m_emit != 0) {
+    if constexpr (KIND == KIND_INTERSECT) {
+        // matches are rare: visit only the set bits (the item's position in A / B follows from the
+        // took-A mask, no walk needed)
+        unsigned m = m_emit;
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const int na_before = __popc(m_ta & ((1u << k) - 1u));
+            const int ai = ai0 + na_before, bi = bi0 + k - na_before;
+            ek[off] = As64[ai];
+            if constexpr (HAS_VAL) {
+                const V x = __ldg(reinterpret_cast<const V*>(p.a_val) + g.a0 + ai);   // only matched values are read
+                V y = __ldg(reinterpret_cast<const V*>(p.b_val) + g.b0 + bi);
+                if (p.negate_b) y = (V)(-y);
+                ev[off] = value_op<V, VO>(p.op, x, y);
+            }
+            if constexpr (SEAM) {
+                epa[off] = g.a0 + ai;
+                epb[off] = g.b0 + bi;
+            }
+            ++off;
+        }
+        return;
+    } else {
         const V* Av = STAGE_VALS ? reinterpret_cast<const V*>(buf + g.offAv) : nullptr;
         const V* Bv = STAGE_VALS ? reinterpret_cast<const V*>(buf + g.offBv) : nullptr;
         int ai = ai0, bi = bi0;
@@ -613,31 +636,20 @@ setop_kernel(const SetopParams p) {
             if (e) {
                 ek[off] = ta ? As64[ai] : Bs64[bi];
                 if constexpr (HAS_VAL) {
-                    V x, y;
-                    if constexpr (STAGE_VALS) {
-                        x = ta ? Av[ai] : V(0);
-                        y = (!ta || eq) ? Bv[bi] : V(0);
-                        if (p.negate_b && (!ta || eq)) y = (V)(-y);
-                    } else {   // intersection: only matched values are ever read
-                        x = __ldg(reinterpret_cast<const V*>(p.a_val) + g.a0 + ai);
-                        y = __ldg(reinterpret_cast<const V*>(p.b_val) + g.b0 + bi);
-                        if (p.negate_b) y = (V)(-y);
-                    }
-                    if constexpr (KIND == KIND_UNION && sizeof(VO) == sizeof(V)) {
+                    const V x = ta ? Av[ai] : V(0);
+                    V y = (!ta || eq) ? Bv[bi] : V(0);
+                    if (p.negate_b && (!ta || eq)) y = (V)(-y);
+                    if constexpr (sizeof(VO) == sizeof(V)) {
                         // assignment semantics: the stored b wins, a survives where b is absent
                         ev[off] = p.op == SPB_OVERRIDE ? (VO)((!ta || eq) ? y : x) : value_op<V, VO>(p.op, x, y);
                     } else {
                         ev[off] = value_op<V, VO>(p.op, x, y);
                     }
                 }
-                if constexpr (SEAM && KIND == KIND_UNION) slut[off] = ta ? (eq ? 2 : 0) : 1;
-                if constexpr (SEAM && KIND == KIND_INTERSECT) {
-                    epa[off] = g.a0 + ai;
-                    epb[off] = g.b0 + bi;
-                }
+                if constexpr (SEAM) slut[off] = ta ? (eq ? 2 : 0) : 1;
                 ++off;
             }
-            if constexpr (SEAM && KIND == KIND_UNION) {
+            if constexpr (SEAM) {
                 if (k < steps) {
                     if (ta) {
                         if (p.a_only) p.a_only[g.a0 + ai] = eq ? 0 : 1;
