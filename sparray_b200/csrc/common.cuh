@@ -41,6 +41,9 @@ extern unsigned long long g_launches;
 // [kWsMiscBytes, ...) epoch-tagged look-back state words.  Only state words are ever
 // written to the second region, so a stale word can never alias a live epoch.
 constexpr size_t kWsMiscBytes = 1u << 20;
+// A few self-resetting counters sit behind the state words: zero whenever no launch is in flight
+// (the kernel that consumes one puts it back to zero), so they need no memset per call either.
+constexpr size_t kWsCounterBytes = 256;
 int workspace_reserve(spb_workspace* ws, size_t state_bytes, cudaStream_t stream);   // workspace.cu
 int workspace_next_epoch(spb_workspace* ws, cudaStream_t stream, uint32_t* epoch);
 int workspace_reserve_payload(spb_workspace* ws, size_t bytes, cudaStream_t stream);
@@ -48,6 +51,7 @@ int workspace_reserve_state16(spb_workspace* ws, size_t bytes, cudaStream_t stre
 int device_sm_count();
 inline uint64_t* ws_state(spb_workspace* ws) { return reinterpret_cast<uint64_t*>((char*)ws->dev + kWsMiscBytes); }
 inline char* ws_misc(spb_workspace* ws) { return (char*)ws->dev; }
+inline unsigned long long* ws_counters(spb_workspace* ws) { return reinterpret_cast<unsigned long long*>((char*)ws->dev + ws->bytes); }
 
 constexpr int kWarp = 32;
 constexpr int64_t kKeyMax = INT64_MAX;

@@ -125,9 +125,9 @@ constexpr int kNT = 256;   // threads per CTA
 constexpr int key_region_bytes(int vt) { return (kNT * vt + 4) * 8 + 128 + vt * 8; }
 
 // ---- launch 1: merge-path split of every tile + its staging descriptor ------------------------
-// One warp per tile: two 32-ary merge-path searches (the tile's two diagonals), then lane 0
-// works out everything the persistent kernel needs to stage the tile -- so that kernel's
-// prefetching warp only loads 128 bytes and issues the copies.
+// Half-warps search the tile diagonals (16-ary, bracketed around the proportional guess); one thread
+// per tile then works out everything the merge kernel needs to stage the tile -- so that kernel's
+// staging warp only loads 128 bytes and issues the copies.
 //   word 0..4 : the Geom record (a0, b0, an|bn, offA|offB, offAv|offBv)
 //   word 5..8 : 16-byte aligned global source of the TMA copy of A keys, B keys, A values, B values
 //   word 9    : 4 x 16 bit  destination offsets inside the tile buffer
@@ -150,14 +150,14 @@ struct PartitionParams {
 
 constexpr int64_t kGuessWindow = 8192;
 
-// 16 lanes per diagonal (two diagonals per warp): ~6 dependent rounds of 16 probe pairs each
-__global__ void __launch_bounds__(256) merge_splits_kernel(const PartitionParams p, int64_t* __restrict__ splits) {
-    const int64_t gthread = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    int64_t w = gthread >> 4;                    // diagonal index 0..ntiles
+// Diagonals (tile boundaries) per CTA of the partition kernel: 16 half-warps search 16 consecutive
+// diagonals, then 15 threads turn the 15 tiles between them into staging descriptors.
+constexpr int kPartTiles = 15;
+
+// 16 lanes per diagonal (two diagonals per warp): a bracket probe + ~4 dependent rounds of 16 probe pairs
+__device__ __forceinline__ int64_t merge_split_halfwarp(const PartitionParams& p, int64_t w) {
     const int lane16 = threadIdx.x & 15;
     const unsigned gmask = 0xffffu << (threadIdx.x & 16);
-    const bool active = w <= p.ntiles;
-    if (!active) w = p.ntiles;                   // keep the half-warp converged on a valid diagonal
     const int64_t total = p.na + p.nb;
     int64_t d = w * (int64_t)p.tile_items;
     if (d > total) d = total;
@@ -196,18 +196,25 @@ __global__ void __launch_bounds__(256) merge_splits_kernel(const PartitionParams
         lo = m_last_true + 1;
         if (c < 16) hi = m_first_false;
     }
-    if (active && lane16 == 0) splits[w] = lo;
+    return lo;
 }
 
-__global__ void __launch_bounds__(256) merge_partition_kernel(const PartitionParams p, const int64_t* __restrict__ splits) {
-    cudaGridDependencySynchronize();               // splits come from the previous launch
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= p.ntiles) return;
+__global__ void __launch_bounds__(256) merge_partition_kernel(const PartitionParams p) {
+    __shared__ int64_t s_split[16];
+    {
+        int64_t w = (int64_t)blockIdx.x * kPartTiles + (threadIdx.x >> 4);   // diagonal index 0..ntiles
+        if (w > p.ntiles) w = p.ntiles;              // keep the half-warp converged on a valid diagonal
+        const int64_t sp = merge_split_halfwarp(p, w);
+        if ((threadIdx.x & 15) == 0) s_split[threadIdx.x >> 4] = sp;
+    }
+    __syncthreads();
+    const int64_t t = (int64_t)blockIdx.x * kPartTiles + threadIdx.x;
+    if (threadIdx.x >= kPartTiles || t >= p.ntiles) return;
     const int kKeyReg = p.key_reg;
     const int64_t total = p.na + p.nb;
     const int64_t d0 = t * (int64_t)p.tile_items;
     const int64_t d1 = (d0 + p.tile_items < total) ? d0 + p.tile_items : total;
-    const int64_t a0 = splits[t], a1 = splits[t + 1];
+    const int64_t a0 = s_split[threadIdx.x], a1 = s_split[threadIdx.x + 1];
     const int64_t b0 = d0 - a0, b1 = d1 - a1;
     // indices [x0-1, x1] (one halo key either side), values [x0, x1) (+1 for B: partner of the last A)
     const int64_t ga_lo = a0 > 0 ? a0 - 1 : 0, ga_hi = a1 < p.na ? a1 + 1 : p.na;
@@ -686,6 +693,7 @@ __global__ void __launch_bounds__(256) merge_reorder_kernel(const SetopParams p)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t first_tile = (int64_t)blockIdx.x * 8;
     cudaGridDependencySynchronize();               // chunks and counts come from the previous launch
+    if (blockIdx.x == 0 && tid == 0) *p.slot_counter = 0;   // every reservation is done: ready for the next call
     int64_t acc = 0;
     for (int64_t t = tid; t < first_tile; t += 256) acc += __ldg(p.tile_cnt + t);
 #pragma unroll
@@ -743,6 +751,7 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     size_t off_tbpos = off_tapos + (SEAM ? cap * 8 : 0);
     size_t payload_bytes = KIND == KIND_INTERSECT ? off_tbpos + (SEAM ? cap * 8 : 0) : off_slot;
     rc = workspace_reserve_payload(ws, payload_bytes, stream);
+    if (rc) return rc;
     rc = workspace_next_epoch(ws, stream, &p.epoch);
     if (rc) return rc;
     p.state = ws_state(ws);
@@ -768,21 +777,16 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     pp.key_reg = C::L::kKeyReg;
     pp.desc = reinterpret_cast<uint64_t*>(ws->payload);
     char* pay = reinterpret_cast<char*>(ws->payload);
-    int64_t* splits = reinterpret_cast<int64_t*>(pay + off_splits);
     if (KIND == KIND_INTERSECT) {
         p.tile_slot = reinterpret_cast<int64_t*>(pay + off_slot);
         p.tile_cnt = reinterpret_cast<int*>(pay + off_cnt);
-        p.slot_counter = reinterpret_cast<unsigned long long*>(pay + off_counter);
+        p.slot_counter = ws_counters(ws);          // zero between calls: the reorder pass resets it
         p.tmp_idx = reinterpret_cast<int64_t*>(pay + off_tidx);
         p.tmp_val = pay + off_tval;
         p.tmp_apos = reinterpret_cast<int64_t*>(pay + off_tapos);
         p.tmp_bpos = reinterpret_cast<int64_t*>(pay + off_tbpos);
-        SPB_CUDA_TRY(cudaMemsetAsync(p.slot_counter, 0, 8, stream));
     }
-    merge_splits_kernel<<<(unsigned)ceil_div((ntiles + 1) * 16, 256), 256, 0, stream>>>(pp, splits);
-    SPB_LAUNCHED(1);
-    SPB_CUDA_TRY(launch_pdl(merge_partition_kernel, dim3((unsigned)ceil_div(ntiles, 256)), dim3(256), 0, stream, pp,
-                            (const int64_t*)splits));
+    merge_partition_kernel<<<(unsigned)ceil_div(ntiles, kPartTiles), 256, 0, stream>>>(pp);
     SPB_LAUNCHED(1);
     SPB_CUDA_TRY(launch_pdl(kern, dim3((unsigned)ntiles), dim3(C::kThreads), (size_t)smem, stream, p));
     SPB_LAUNCHED(1);

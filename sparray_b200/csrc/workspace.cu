@@ -8,15 +8,15 @@ int workspace_reserve(spb_workspace* ws, size_t state_bytes, cudaStream_t stream
     if (!ws) return SPB_ERR_BAD_ARG;
     const size_t bytes = kWsMiscBytes + state_bytes;
     if (ws->bytes >= bytes && ws->dev) return SPB_OK;
-    size_t want = bytes + state_bytes / 2 + (1u << 20);
+    size_t want = (bytes + state_bytes / 2 + (1u << 20) + 255) & ~(size_t)255;
     if (ws->dev) {
         SPB_CUDA_TRY(cudaStreamSynchronize(stream));
         SPB_CUDA_TRY(cudaFree(ws->dev));
         ws->dev = nullptr;
         ws->bytes = 0;
     }
-    SPB_CUDA_TRY(cudaMalloc(&ws->dev, want));
-    SPB_CUDA_TRY(cudaMemsetAsync(ws->dev, 0, want, stream));
+    SPB_CUDA_TRY(cudaMalloc(&ws->dev, want + kWsCounterBytes));
+    SPB_CUDA_TRY(cudaMemsetAsync(ws->dev, 0, want + kWsCounterBytes, stream));
     ws->bytes = want;
     ws->epoch = 0;
     return SPB_OK;
