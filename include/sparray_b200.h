@@ -218,8 +218,10 @@ int spb_rekey_sort(int dtype, const int64_t* idx, const void* val, int64_t n,
  * Every element adds into acc[new_key] (float64 atomics; acc: cells doubles, touched: cells bytes,
  * 16-byte aligned, both zeroed here), then the touched cells are emitted in key order (explicit
  * zeros survive).  Strides as in spb_rekey_sort.  out_idx / out_sums: min(n, cells) slots.  The
- * order of the additions is not fixed, so sums may differ in the last bits from run to run. */
-int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val, int64_t n,
+ * order of the additions is not fixed, so sums may differ in the last bits from run to run.
+ * n_dev (may be NULL): device int64 holding the real element count when the producer's count has
+ * not been read back (the out_count of a binop on the same stream); n is then its upper bound. */
+int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev,
                        int ndim, const int64_t* in_strides_host, const int64_t* out_strides_host,
                        int64_t cells, double* acc, uint8_t* touched,
                        int64_t* out_idx, double* out_sums, int64_t* out_count,

@@ -98,10 +98,12 @@ def len_range(start, stop, step):
 _WIDEN = {torch.bool: torch.int32, torch.uint8: torch.int32, torch.int8: torch.int32, torch.int16: torch.int32}
 
 
-def setop_binop(kind, op, a_idx, a_val, b_idx, b_val):
+def setop_binop(kind, op, a_idx, a_val, b_idx, b_val, lazy=False):
     """kind: 'union' | 'intersect'.  Values must already share a dtype.  The fused kernels
     are instantiated for 4- and 8-byte values; bool / 8- / 16-bit operands are widened to
-    int32 for the merge and narrowed back (bool: + is OR, * is AND, as in numpy)."""
+    int32 for the merge and narrowed back (bool: + is OR, * is AND, as in numpy).
+    Returns (indices, values, None), or with lazy=True possibly (worst-case-sized indices,
+    values, device count): the count is not read back, so the call does not synchronise."""
     require_cuda()
     assert a_val.dtype == b_val.dtype
     orig = a_val.dtype
@@ -116,11 +118,14 @@ def setop_binop(kind, op, a_idx, a_val, b_idx, b_val):
     fn = lib.spb_union_binop if kind == "union" else lib.spb_intersect_binop
     check(fn(dt.BINOPS[op], dt.spb_dtype(a_val.dtype), ptr(a_idx), ptr(a_val), na, ptr(b_idx), ptr(b_val), nb,
              ptr(out_idx), ptr(out_val), ptr(cnt), workspace(), stream()))
+    narrow = orig in _WIDEN and op not in dt.COMPARISONS
+    if lazy and not narrow and cap:
+        return out_idx, out_val, cnt
     n = _count(cnt)
     out_idx, out_val = _trim(out_idx, n), _trim(out_val, n)
-    if orig in _WIDEN and op not in dt.COMPARISONS:
+    if narrow:
         out_val = cast(out_val, orig)
-    return out_idx, out_val
+    return out_idx, out_val, None
 
 
 # ---- section 3: maps, conversion, lookup -----------------------------------------------------
@@ -278,24 +283,40 @@ def transpose(idx, val, shape, axes):
 DENSE_SUM_MAX_CELLS = 1 << 26      # 512 MiB of float64 accumulators
 
 
-def sum_axis(idx, val, shape, axis):
-    """(new sorted unique flat indices, float64 sums) -- flat.py:617-625.
+DENSE_SUM_ANY_N_CELLS = 1 << 22    # below this the dense path is taken whatever the element count
+
+
+def dense_sum_cells(shape, axis):
+    """Cell count of sum(axis)'s result if the dense-accumulator path applies whatever nnz is, else 0."""
+    from . import _plan
+    if axis == len(shape) - 1:
+        return 0
+    cells = _plan.prod(shape) // max(int(shape[axis]), 1)
+    return cells if 0 < cells <= DENSE_SUM_ANY_N_CELLS else 0
+
+
+def sum_axis(idx, val, shape, axis, n_dev=None):
+    """(new sorted unique flat indices, float64 sums, device count or None) -- flat.py:617-625.
     last axis: segmented reduce, no sort; otherwise a dense float64 accumulator when the reduced
-    array is small enough to hold (no sort either), else re-key + radix sort + segmented reduce."""
+    array is small enough to hold (no sort either), else re-key + radix sort + segmented reduce.
+    The dense path leaves its element count on the device (worst-case-sized outputs); n_dev is the
+    device count of a producer that was not read back either (only valid when dense_sum_cells())."""
     from . import _plan
     plan = _plan.axis_sum_plan(shape, axis)
     if plan[0] == "last":
-        return reduce_by_key(idx, val, plan[1])
+        assert n_dev is None
+        return reduce_by_key(idx, val, plan[1]) + (None,)
     _, in_s, out_s, bits = plan
     n = idx.numel()
     cells = _plan.prod(shape) // int(shape[axis])
-    if n and cells <= DENSE_SUM_MAX_CELLS and cells <= 64 * n + (1 << 22):
-        return axis_sum_dense(idx, val, in_s, out_s, cells)
+    if n and cells <= DENSE_SUM_MAX_CELLS and cells <= 64 * n + DENSE_SUM_ANY_N_CELLS:
+        return axis_sum_dense(idx, val, in_s, out_s, cells, n_dev)
+    assert n_dev is None
     keys, vals = rekey_sort(idx, val, in_s, out_s, 1, bits)
-    return reduce_by_key(keys, vals, 1)
+    return reduce_by_key(keys, vals, 1) + (None,)
 
 
-def axis_sum_dense(idx, val, in_strides, out_strides, cells):
+def axis_sum_dense(idx, val, in_strides, out_strides, cells, n_dev=None):
     require_cuda()
     n = idx.numel()
     cap = min(n, cells)
@@ -307,11 +328,10 @@ def axis_sum_dense(idx, val, in_strides, out_strides, cells):
     ndim = len(in_strides)
     ins = (ctypes.c_int64 * ndim)(*in_strides)
     outs = (ctypes.c_int64 * ndim)(*out_strides)
-    check(lib.spb_axis_sum_dense(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), n, ndim,
+    check(lib.spb_axis_sum_dense(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), n, ptr(n_dev), ndim,
                                  ctypes.cast(ins, ctypes.c_void_p), ctypes.cast(outs, ctypes.c_void_p), int(cells),
                                  ptr(acc), ptr(touched), ptr(out_idx), ptr(out_sums), ptr(cnt), workspace(), stream()))
-    k = _count(cnt)
-    return _trim(out_idx, k), _trim(out_sums, k)
+    return out_idx, out_sums, cnt
 
 
 def canonicalize(idx, val, max_key=None):

@@ -395,8 +395,13 @@ namespace spb {
 
 template <typename T>
 __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
-                                                              int64_t n, const Rekey rk, double* __restrict__ acc,
+                                                              int64_t n, const int64_t* __restrict__ n_dev,
+                                                              const Rekey rk, double* __restrict__ acc,
                                                               uint8_t* __restrict__ touched) {
+    if (n_dev) {                       // the producer's count never left the device; n is its upper bound
+        const int64_t m = *n_dev;
+        n = m < n ? m : n;
+    }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t key = apply_rekey(__ldcs(idx + i), rk);
         atomicAdd(acc + key, (double)__ldcs(val + i));
@@ -434,7 +439,7 @@ __global__ void __launch_bounds__(256) select_touched_kernel(const double* __res
 
 }  // namespace spb
 
-extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val, int64_t n, int ndim,
+extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev, int ndim,
                                   const int64_t* in_strides, const int64_t* out_strides, int64_t cells, double* acc,
                                   uint8_t* touched, int64_t* out_idx, double* out_sums, int64_t* out_count,
                                   spb_workspace* ws, spb_stream_t stream) {
@@ -456,7 +461,7 @@ extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val
     int64_t blocks = ceil_div(n, 256 * 4);
     if (blocks > 148 * 16) blocks = 148 * 16;
 #define SPB_ACC(T)                                                                                            \
-    axis_accumulate_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(idx, (const T*)val, n, rk, acc, touched); \
+    axis_accumulate_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(idx, (const T*)val, n, n_dev, rk, acc, touched); \
     break
     switch (dtype) {
         case SPB_F32: SPB_ACC(float);

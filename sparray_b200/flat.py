@@ -100,13 +100,63 @@ class FlatSparray(_BaseSparray):
         else:
             self.shape = tuple(int(s) for s in shape)
             assert np.prod(self.shape, dtype=object) >= len(data)
-        self.indices = indices
-        self.data = data
+        self._pending = None
+        self._indices = indices
+        self._data = data
+
+    # -- lazily counted results ---------------------------------------------------------------
+    # A kernel with a data-dependent output size writes worst-case-sized buffers and leaves the
+    # element count on the device.  Reading the count is the op's one host synchronisation, so it
+    # is put off until somebody looks at `indices` / `data` / `nnz`: a consumer that can take the
+    # count from the device (sum over an axis through the dense accumulator) chains on the stream
+    # without the host ever waiting.
+    @classmethod
+    def _from_kernel(cls, idx, val, cnt, shape):
+        """(indices, values, device count or None) of a kernel wrapper -> canonical FlatSparray."""
+        if cnt is None:
+            return cls(idx, val, shape=shape, is_canonical=True)
+        self = cls.__new__(cls)
+        self.shape = tuple(int(s) for s in shape)
+        self._pending = (idx, val, cnt)
+        self._indices = self._data = None
+        return self
+
+    def _resolve(self):
+        idx, val, cnt = self._pending
+        n = _k._count(cnt)
+        self._indices, self._data = _k._trim(idx, n), _k._trim(val, n)
+        self._pending = None
+
+    @property
+    def indices(self):
+        if self._pending is not None:
+            self._resolve()
+        return self._indices
+
+    @indices.setter
+    def indices(self, value):
+        if self._pending is not None:
+            self._resolve()
+        self._indices = value
+
+    @property
+    def data(self):
+        if self._pending is not None:
+            self._resolve()
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        if self._pending is not None:
+            self._resolve()
+        self._data = value
 
     # -- basic properties ---------------------------------------------------------------------
     @property
     def dtype(self):
-        return dt.np_dtype(self.data.dtype)
+        if self._pending is not None:
+            return dt.np_dtype(self._pending[1].dtype)
+        return dt.np_dtype(self._data.dtype)
 
     def getnnz(self):
         """Get the count of explicitly-stored values"""
@@ -318,7 +368,7 @@ class FlatSparray(_BaseSparray):
             if vals.numel() != n:
                 raise ValueError("shape mismatch: value array of size %d could not be broadcast to indexing "
                                  "result of size %d" % (vals.numel(), n))
-        idx, data = _k.setop_binop("union", "override", self.indices, self.data, flat_idx, vals)
+        idx, data, _ = _k.setop_binop("union", "override", self.indices, self.data, flat_idx, vals)
         self.indices, self.data = idx, data
 
     # -- sparse (op) sparse helpers (flat.py:409-434) ---------------------------------------------
@@ -338,14 +388,14 @@ class FlatSparray(_BaseSparray):
     def _pairwise_sparray(self, other, op):
         """op(sparse, sparse) -> sparse on the UNION of the index sets; one fused kernel."""
         a_val, b_val = self._promoted(other, op)
-        idx, val = _k.setop_binop("union", op, self.indices, a_val, other.indices, b_val)
-        return FlatSparray(idx, val, self.shape, is_canonical=True)
+        idx, val, cnt = _k.setop_binop("union", op, self.indices, a_val, other.indices, b_val, lazy=True)
+        return FlatSparray._from_kernel(idx, val, cnt, self.shape)
 
     def _pairwise_sparray_fixed_zero(self, other, op):
         """op(sparse, sparse) -> sparse on the INTERSECTION (op(x, 0) == 0); one fused kernel."""
         a_val, b_val = self._promoted(other, op)
-        idx, val = _k.setop_binop("intersect", op, self.indices, a_val, other.indices, b_val)
-        return FlatSparray(idx, val, self.shape, is_canonical=True)
+        idx, val, cnt = _k.setop_binop("intersect", op, self.indices, a_val, other.indices, b_val, lazy=True)
+        return FlatSparray._from_kernel(idx, val, cnt, self.shape)
 
     # -- broadcasting and dense operands (flat.py:436-472) ------------------------------------------
     def _broadcast(self, shape):
@@ -598,8 +648,13 @@ class FlatSparray(_BaseSparray):
                 return np.bool_(total != 0)
             return dtype.type(total)
         # float64 output whatever the input dtype, like np.bincount(weights=)
-        new_idx, new_val = _k.sum_axis(self.indices, self.data, self.shape, axis)
-        return FlatSparray(new_idx, new_val, shape=new_shape, is_canonical=True)
+        if self._pending is not None and _k.dense_sum_cells(self.shape, axis):
+            # the producer's count is still on the device and this path does not need it on the host
+            p_idx, p_val, p_cnt = self._pending
+            new_idx, new_val, cnt = _k.sum_axis(p_idx, p_val, self.shape, axis, n_dev=p_cnt)
+        else:
+            new_idx, new_val, cnt = _k.sum_axis(self.indices, self.data, self.shape, axis)
+        return FlatSparray._from_kernel(new_idx, new_val, cnt, new_shape)
 
     # -- unary data ops (flat.py:677-739) -----------------------------------------------------------
     def __abs__(self):

@@ -46,7 +46,7 @@ class CudaOps:
             common = dt.promote(a_val.dtype, b_val.dtype)
             a_val = self.k.cast(a_val, common) if a_val.dtype != common else a_val
             b_val = self.k.cast(b_val, common) if b_val.dtype != common else b_val
-        return self.k.setop_binop(kind, op, a_idx, a_val, b_idx, b_val)
+        return self.k.setop_binop(kind, op, a_idx, a_val, b_idx, b_val)[:2]
 
     def reduce_by_key(self, keys, vals, divisor=1):
         return self.k.reduce_by_key(keys, vals, divisor)
