@@ -215,16 +215,16 @@ int spb_rekey_sort(int dtype, const int64_t* idx, const void* val, int64_t n,
                    spb_workspace* ws, spb_stream_t stream);
 
 /* sum(axis != last) when prod(new_shape) (= cells) is small enough to hold densely: no sort.
- * Every element adds into acc[new_key] (float64 atomics; acc: cells doubles, touched: cells bytes,
- * 16-byte aligned, both zeroed here), then the touched cells are emitted in key order (explicit
- * zeros survive).  Strides as in spb_rekey_sort.  out_idx / out_sums: min(n, cells) slots.  The
- * order of the additions is not fixed, so sums may differ in the last bits from run to run.
+ * Every element adds into acc[new_key] (float64 atomics; cells doubles + cells flag bytes live in
+ * the workspace, all-zero between calls: the emitting pass zeroes what it reads), then the touched
+ * cells are emitted in key order (explicit zeros survive).  Strides as in spb_rekey_sort.
+ * out_idx / out_sums: min(n, cells) slots.  The order of the additions is not fixed, so sums may
+ * differ in the last bits from run to run.
  * n_dev (may be NULL): device int64 holding the real element count when the producer's count has
  * not been read back (the out_count of a binop on the same stream); n is then its upper bound. */
 int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev,
                        int ndim, const int64_t* in_strides_host, const int64_t* out_strides_host,
-                       int64_t cells, double* acc, uint8_t* touched,
-                       int64_t* out_idx, double* out_sums, int64_t* out_count,
+                       int64_t cells, int64_t* out_idx, double* out_sums, int64_t* out_count,
                        spb_workspace* ws, spb_stream_t stream);
 
 /* ---- 6. __getitem__: flat.py:254-325, 366-393 ---------------------------------- */

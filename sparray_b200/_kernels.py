@@ -320,8 +320,6 @@ def axis_sum_dense(idx, val, in_strides, out_strides, cells, n_dev=None):
     require_cuda()
     n = idx.numel()
     cap = min(n, cells)
-    acc = torch.empty(cells, dtype=torch.float64, device=idx.device)
-    touched = torch.empty(cells, dtype=torch.uint8, device=idx.device)
     out_idx = torch.empty(cap, dtype=torch.int64, device=idx.device)
     out_sums = torch.empty(cap, dtype=torch.float64, device=idx.device)
     cnt = torch.empty(1, dtype=torch.int64, device=idx.device)
@@ -330,7 +328,7 @@ def axis_sum_dense(idx, val, in_strides, out_strides, cells, n_dev=None):
     outs = (ctypes.c_int64 * ndim)(*out_strides)
     check(lib.spb_axis_sum_dense(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), n, ptr(n_dev), ndim,
                                  ctypes.cast(ins, ctypes.c_void_p), ctypes.cast(outs, ctypes.c_void_p), int(cells),
-                                 ptr(acc), ptr(touched), ptr(out_idx), ptr(out_sums), ptr(cnt), workspace(), stream()))
+                                 ptr(out_idx), ptr(out_sums), ptr(cnt), workspace(), stream()))
     return out_idx, out_sums, cnt
 
 

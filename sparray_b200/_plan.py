@@ -2,6 +2,8 @@
 axes can be merged, which strides the kernel needs, and how few key bits have
 to be sorted.  Pure Python integers; importable and testable without CUDA."""
 
+import functools
+
 MAX_REKEY_DIMS = 8
 
 
@@ -60,6 +62,11 @@ def rekey_strides(shape, out_axes):
 
 
 def transpose_plan(shape, axes):
+    return _transpose_plan(tuple(int(s) for s in shape), tuple(int(a) for a in axes))
+
+
+@functools.lru_cache(maxsize=256)
+def _transpose_plan(shape, axes):
     """Plan for FlatSparray.transpose: (in_strides, out_strides, sort_divisor, sort_bits).
 
     The input is sorted by the old key.  An LSD radix sort is stable, so if the
@@ -82,6 +89,11 @@ def transpose_plan(shape, axes):
 
 
 def axis_sum_plan(shape, axis):
+    return _axis_sum_plan(tuple(int(s) for s in shape), int(axis))
+
+
+@functools.lru_cache(maxsize=256)
+def _axis_sum_plan(shape, axis):
     """Plan for sum(axis): ('last', divisor) when the reduced axis is the last one
     (the remaining key stays sorted: no sort at all), else ('sort', in_strides,
     out_strides, sort_bits) -- dropping a middle axis interleaves the later axes,

@@ -409,7 +409,9 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
     }
 }
 
-__global__ void __launch_bounds__(256) select_touched_kernel(const double* __restrict__ acc, const uint8_t* __restrict__ touched,
+// Emits the touched cells in key order and puts every cell it emitted back to zero, so the
+// accumulator slab is all-zero again when the call is over (no memset per call).
+__global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict__ acc, uint8_t* __restrict__ touched,
                                                              int64_t cells, int64_t* __restrict__ out_idx,
                                                              double* __restrict__ out_val, int64_t* out_count,
                                                              uint64_t* state, uint32_t epoch) {
@@ -418,13 +420,18 @@ __global__ void __launch_bounds__(256) select_touched_kernel(const double* __res
     const int64_t first = tile * (256 * VT) + (int64_t)threadIdx.x * VT;
     unsigned bits = 0;
     if (first + VT <= cells) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(touched + first);     // 16 flags at once (first % 16 == 0)
+        uint4* const flags = reinterpret_cast<uint4*>(touched + first);         // 16 flags at once (first % 16 == 0)
+        const uint4 raw = *flags;
         const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
         for (int k = 0; k < VT; ++k) bits |= (((w[k >> 2] >> (8 * (k & 3))) & 0xffu) ? 1u : 0u) << k;
+        if (bits) *flags = make_uint4(0, 0, 0, 0);
     } else {
         for (int k = 0; k < VT; ++k)
-            if (first + k < cells && touched[first + k]) bits |= 1u << k;
+            if (first + k < cells && touched[first + k]) {
+                bits |= 1u << k;
+                touched[first + k] = 0;
+            }
     }
     int64_t off = compact_offset_256(__popc(bits), state, epoch, tile, tile == gridDim.x - 1, out_count);
 #pragma unroll
@@ -432,6 +439,7 @@ __global__ void __launch_bounds__(256) select_touched_kernel(const double* __res
         if (bits & (1u << k)) {
             out_idx[off] = first + k;
             out_val[off] = acc[first + k];
+            acc[first + k] = 0.0;
             ++off;
         }
     }
@@ -440,15 +448,14 @@ __global__ void __launch_bounds__(256) select_touched_kernel(const double* __res
 }  // namespace spb
 
 extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev, int ndim,
-                                  const int64_t* in_strides, const int64_t* out_strides, int64_t cells, double* acc,
-                                  uint8_t* touched, int64_t* out_idx, double* out_sums, int64_t* out_count,
+                                  const int64_t* in_strides, const int64_t* out_strides, int64_t cells,
+                                  int64_t* out_idx, double* out_sums, int64_t* out_count,
                                   spb_workspace* ws, spb_stream_t stream) {
     using namespace spb;
     if (n < 0 || cells < 0 || ndim < 1 || ndim > kMaxRekeyDims || !in_strides || !out_strides || !out_count)
         return SPB_ERR_BAD_ARG;
     if (n == 0 || cells == 0) return (int)cudaMemsetAsync(out_count, 0, 8, stream);
-    if (!idx || !val || !acc || !touched || !out_idx || !out_sums) return SPB_ERR_BAD_ARG;
-    if ((reinterpret_cast<uintptr_t>(touched) & 15) != 0) return SPB_ERR_BAD_ARG;
+    if (!idx || !val || !out_idx || !out_sums || !ws) return SPB_ERR_BAD_ARG;
     Rekey rk{};
     rk.ndim = ndim;
     for (int ax = 0; ax < ndim; ++ax) {
@@ -456,8 +463,14 @@ extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val
         rk.in_div[ax] = make_fastdiv((uint64_t)in_strides[ax]);
         rk.out_mul[ax] = out_strides[ax];
     }
-    SPB_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)cells * sizeof(double), stream));
-    SPB_CUDA_TRY(cudaMemsetAsync(touched, 0, (size_t)cells, stream));
+    // accumulators (cells doubles) then flags (cells bytes) in the workspace's self-cleaning slab
+    const size_t acc_bytes = ((size_t)cells * sizeof(double) + 255) & ~(size_t)255;
+    {
+        const int rc0 = workspace_reserve_accum(ws, acc_bytes + (size_t)cells, stream);
+        if (rc0) return rc0;
+    }
+    double* const acc = reinterpret_cast<double*>(ws->accum);
+    uint8_t* const touched = reinterpret_cast<uint8_t*>(ws->accum) + acc_bytes;
     int64_t blocks = ceil_div(n, 256 * 4);
     if (blocks > 148 * 16) blocks = 148 * 16;
 #define SPB_ACC(T)                                                                                            \

@@ -53,6 +53,22 @@ int workspace_reserve_state16(spb_workspace* ws, size_t bytes, cudaStream_t stre
     return SPB_OK;
 }
 
+int workspace_reserve_accum(spb_workspace* ws, size_t bytes, cudaStream_t stream) {
+    if (!ws) return SPB_ERR_BAD_ARG;
+    if (ws->accum_bytes >= bytes && ws->accum) return SPB_OK;
+    if (ws->accum) {
+        SPB_CUDA_TRY(cudaStreamSynchronize(stream));
+        SPB_CUDA_TRY(cudaFree(ws->accum));
+        ws->accum = nullptr;
+        ws->accum_bytes = 0;
+    }
+    const size_t want = (bytes + bytes / 4 + (1u << 20) + 255) & ~(size_t)255;
+    SPB_CUDA_TRY(cudaMalloc(&ws->accum, want));
+    SPB_CUDA_TRY(cudaMemsetAsync(ws->accum, 0, want, stream));     // zero from here on: users clean up after themselves
+    ws->accum_bytes = want;
+    return SPB_OK;
+}
+
 // next launch epoch (1 .. 2^14-1); re-zero the state words when the counter wraps
 int workspace_next_epoch(spb_workspace* ws, cudaStream_t stream, uint32_t* epoch) {
     ws->epoch += 1;
@@ -93,6 +109,8 @@ int spb_workspace_create(spb_workspace** ws) {
     w->payload_bytes = 0;
     w->state16 = nullptr;
     w->state16_bytes = 0;
+    w->accum = nullptr;
+    w->accum_bytes = 0;
     *ws = w;
     return SPB_OK;
 }
@@ -102,6 +120,7 @@ int spb_workspace_destroy(spb_workspace* ws) {
     if (ws->dev) cudaFree(ws->dev);
     if (ws->payload) cudaFree(ws->payload);
     if (ws->state16) cudaFree(ws->state16);
+    if (ws->accum) cudaFree(ws->accum);
     delete ws;
     return SPB_OK;
 }
