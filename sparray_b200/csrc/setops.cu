@@ -201,6 +201,7 @@ __device__ __forceinline__ int64_t merge_split_halfwarp(const PartitionParams& p
 
 __global__ void __launch_bounds__(256) merge_partition_kernel(const PartitionParams p) {
     __shared__ int64_t s_split[16];
+    cudaGridDependencySynchronize();               // the operands may come from the previous launch
     {
         int64_t w = (int64_t)blockIdx.x * kPartTiles + (threadIdx.x >> 4);   // diagonal index 0..ntiles
         if (w > p.ntiles) w = p.ntiles;              // keep the half-warp converged on a valid diagonal
@@ -692,6 +693,7 @@ __global__ void __launch_bounds__(256) merge_reorder_kernel(const SetopParams p)
     __shared__ int s_cnt[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t first_tile = (int64_t)blockIdx.x * 8;
+    cudaTriggerProgrammaticLaunchCompletion();
     cudaGridDependencySynchronize();               // chunks and counts come from the previous launch
     if (blockIdx.x == 0 && tid == 0) *p.slot_counter = 0;   // every reservation is done: ready for the next call
     int64_t acc = 0;
@@ -786,7 +788,7 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
         p.tmp_apos = reinterpret_cast<int64_t*>(pay + off_tapos);
         p.tmp_bpos = reinterpret_cast<int64_t*>(pay + off_tbpos);
     }
-    merge_partition_kernel<<<(unsigned)ceil_div(ntiles, kPartTiles), 256, 0, stream>>>(pp);
+    SPB_CUDA_TRY(launch_pdl(merge_partition_kernel, dim3((unsigned)ceil_div(ntiles, kPartTiles)), dim3(256), 0, stream, pp));
     SPB_LAUNCHED(1);
     SPB_CUDA_TRY(launch_pdl(kern, dim3((unsigned)ntiles), dim3(C::kThreads), (size_t)smem, stream, p));
     SPB_LAUNCHED(1);

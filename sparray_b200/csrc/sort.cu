@@ -398,6 +398,8 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
                                                               int64_t n, const int64_t* __restrict__ n_dev,
                                                               const Rekey rk, double* __restrict__ acc,
                                                               uint8_t* __restrict__ touched) {
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();   // operands (and n_dev) may come from the previous launch
     if (n_dev) {                       // the producer's count never left the device; n is its upper bound
         const int64_t m = *n_dev;
         n = m < n ? m : n;
@@ -419,6 +421,7 @@ __global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict_
     const int64_t tile = blockIdx.x;
     const int64_t first = tile * (256 * VT) + (int64_t)threadIdx.x * VT;
     unsigned bits = 0;
+    cudaGridDependencySynchronize();   // accumulators come from the previous launch
     if (first + VT <= cells) {
         uint4* const flags = reinterpret_cast<uint4*>(touched + first);         // 16 flags at once (first % 16 == 0)
         const uint4 raw = *flags;
@@ -474,7 +477,8 @@ extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val
     int64_t blocks = ceil_div(n, 256 * 4);
     if (blocks > 148 * 16) blocks = 148 * 16;
 #define SPB_ACC(T)                                                                                            \
-    axis_accumulate_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(idx, (const T*)val, n, n_dev, rk, acc, touched); \
+    SPB_CUDA_TRY(launch_pdl(axis_accumulate_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, idx,   \
+                            (const T*)val, n, n_dev, rk, acc, touched));                                      \
     break
     switch (dtype) {
         case SPB_F32: SPB_ACC(float);
@@ -496,8 +500,8 @@ extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val
     uint32_t epoch;
     rc = workspace_next_epoch(ws, stream, &epoch);
     if (rc) return rc;
-    select_touched_kernel<<<(unsigned)ntiles, 256, 0, stream>>>(acc, touched, cells, out_idx, out_sums, out_count,
-                                                                ws_state(ws), epoch);
+    SPB_CUDA_TRY(launch_pdl(select_touched_kernel, dim3((unsigned)ntiles), dim3(256), 0, stream, acc, touched, cells,
+                            out_idx, out_sums, out_count, ws_state(ws), epoch));
     SPB_LAUNCHED(1);
     return (int)cudaGetLastError();
 }
