@@ -367,3 +367,71 @@ def test_dot_matrix_operands(sp):
     np.testing.assert_allclose(sp.FlatSparray.from_ndarray(T).dot(Bm), T.dot(Bm), rtol=1e-12, atol=1e-12)
     with pytest.raises(ValueError):
         A.dot(np.ones((19, 3)))
+
+
+def _synth_device(torch, n, size, seed):
+    """Sorted unique flat indices in [0, size) with random gaps, and small-integer float64 values
+    (every partial sum is then exact in float64, so the checks below can be bit-exact)."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    gap = max(size // n, 1)
+    steps = torch.randint(1, 2 * gap, (n,), device="cuda", generator=g, dtype=torch.int64)
+    idx = torch.cumsum(steps, 0) - 1
+    idx = idx[idx < size].contiguous()
+    val = torch.randint(-8, 9, (idx.numel(),), device="cuda", generator=g, dtype=torch.int64).to(torch.float64)
+    return idx, val
+
+
+def test_config4_full_size_properties(sp):
+    """BASELINE config 4 at full size (10^6 x 10^6 float64, ~10^8 stored elements): the CPU oracle
+    would need minutes, so parity is checked through size-independent properties --
+    transpose round trip and sortedness, checksums of sums along both axes, SpMV against the row
+    sums and its linearity, a+a / a*a against element-wise maps of the data."""
+    import torch
+    n_side = 10 ** 6
+    idx, val = _synth_device(torch, 100_000_000, n_side * n_side, 7)
+    W = sp.FlatSparray(idx, val, shape=(n_side, n_side), is_canonical=True)
+    n = W.nnz
+    assert n > 90_000_000
+    total = float(val.sum().item())
+
+    # transpose: sorted unique keys, same multiset of values, involution
+    T = W.T
+    assert T.shape == (n_side, n_side) and T.nnz == n
+    assert bool((T.indices[1:] > T.indices[:-1]).all().item())
+    assert float(T.data.sum().item()) == total
+    # element (r, c) of W sits at (c, r) of T: check through a sample of positions
+    pick = torch.arange(0, n, 9973, device="cuda")
+    r, c = idx[pick] // n_side, idx[pick] % n_side
+    pos = torch.searchsorted(T.indices, c * n_side + r)
+    assert bool((T.indices[pos] == c * n_side + r).all().item())
+    assert bool((T.data[pos] == val[pick]).all().item())
+    TT = T.T
+    assert bool((TT.indices == idx).all().item()) and bool((TT.data == val).all().item())
+    del TT
+
+    # axis sums: both keep the grand total; sum(axis=1) equals the row sums of the transpose's sum(axis=0)
+    s1 = W.sum(axis=1)
+    s0 = W.sum(axis=0)
+    assert float(s1.data.sum().item()) == total and float(s0.data.sum().item()) == total
+    t0 = T.sum(axis=0)
+    assert bool((t0.indices == s1.indices).all().item()) and bool((t0.data == s1.data).all().item())
+    del T, t0
+
+    # SpMV: W @ ones are the row sums; linearity with exactly representable operands
+    ones = np.ones(n_side)
+    y1 = W.dot(ones)
+    dense_rows = np.zeros(n_side)
+    dense_rows[to_np(s1.indices)] = to_np(s1.data)
+    np.testing.assert_array_equal(y1, dense_rows)
+    rng = np.random.default_rng(3)
+    x = rng.integers(-4, 5, n_side).astype(np.float64)
+    z = rng.integers(-4, 5, n_side).astype(np.float64)
+    np.testing.assert_array_equal(W.dot(x + z), W.dot(x) + W.dot(z))
+
+    # fused binops against element-wise maps: a + a == 2a on the same pattern, a * a == a^2
+    D = W + W
+    assert D.nnz == n and bool((D.indices == idx).all().item()) and bool((D.data == 2 * val).all().item())
+    del D
+    Q = W * W
+    assert Q.nnz == n and bool((Q.indices == idx).all().item()) and bool((Q.data == val * val).all().item())
