@@ -215,7 +215,7 @@ int spb_rekey_sort(int dtype, const int64_t* idx, const void* val, int64_t n,
                    spb_workspace* ws, spb_stream_t stream);
 
 /* sum(axis != last) when prod(new_shape) (= cells) is small enough to hold densely: no sort.
- * Every element adds into acc[new_key] (float64 atomics; cells doubles + cells flag bytes live in
+ * Every element adds into acc[new_key] (float64 atomics; cells doubles + one flag byte per cell live in
  * the workspace, all-zero between calls: the emitting pass zeroes what it reads), then the touched
  * cells are emitted in key order (explicit zeros survive).  Strides as in spb_rekey_sort.
  * out_idx / out_sums: min(n, cells) slots.  The order of the additions is not fixed, so sums may

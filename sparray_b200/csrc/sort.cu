@@ -407,43 +407,70 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t key = apply_rekey(__ldcs(idx + i), rk);
         atomicAdd(acc + key, (double)__ldcs(val + i));
-        touched[key] = 1;
+        touched[key] = 1;                                      // a flag per cell: explicit zeros survive
     }
 }
 
 // Emits the touched cells in key order and puts every cell it emitted back to zero, so the
-// accumulator slab is all-zero again when the call is over (no memset per call).
+// accumulator slab is all-zero again when the call is over (no memset per call).  One thread owns
+// 64 cells (four 16-byte loads of flag bytes); a tile of 256 threads covers 16 K cells, which keeps
+// the look-back chain short.
 __global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict__ acc, uint8_t* __restrict__ touched,
                                                              int64_t cells, int64_t* __restrict__ out_idx,
                                                              double* __restrict__ out_val, int64_t* out_count,
                                                              uint64_t* state, uint32_t epoch) {
-    constexpr int VT = 16;
     const int64_t tile = blockIdx.x;
-    const int64_t first = tile * (256 * VT) + (int64_t)threadIdx.x * VT;
-    unsigned bits = 0;
+    const int64_t first = (tile * 256 + threadIdx.x) * 64;
     cudaGridDependencySynchronize();   // accumulators come from the previous launch
-    if (first + VT <= cells) {
-        uint4* const flags = reinterpret_cast<uint4*>(touched + first);         // 16 flags at once (first % 16 == 0)
-        const uint4 raw = *flags;
-        const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+    unsigned long long bits = 0;
+    if (first < cells) {               // the flag array is padded to a multiple of 64 (the padding stays zero)
+        uint4* const flags = reinterpret_cast<uint4*>(touched + first);
+        uint4 raw[4];
 #pragma unroll
-        for (int k = 0; k < VT; ++k) bits |= (((w[k >> 2] >> (8 * (k & 3))) & 0xffu) ? 1u : 0u) << k;
-        if (bits) *flags = make_uint4(0, 0, 0, 0);
-    } else {
-        for (int k = 0; k < VT; ++k)
-            if (first + k < cells && touched[first + k]) {
-                bits |= 1u << k;
-                touched[first + k] = 0;
-            }
+        for (int q = 0; q < 4; ++q) raw[q] = flags[q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned w[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                bits |= (unsigned long long)((w[k >> 2] >> (8 * (k & 3))) & 1u) << (16 * q + k);
+            if (raw[q].x | raw[q].y | raw[q].z | raw[q].w) flags[q] = make_uint4(0, 0, 0, 0);
+        }
     }
-    int64_t off = compact_offset_256(__popc(bits), state, epoch, tile, tile == gridDim.x - 1, out_count);
+    const int cnt = __popcll(bits);
+    const int64_t off = compact_offset_256(cnt, state, epoch, tile, tile == gridDim.x - 1, out_count);
+    // Warp-cooperative emission: the warp's outputs are one contiguous run, written 32 at a time (coalesced
+    // whether the cells are nearly all touched or nearly all empty).  Output r of the warp belongs to the
+    // first lane whose inclusive count exceeds r, and is that lane's (r - exclusive count)-th set bit.
+    const int lane = threadIdx.x & 31;
+    int incl = cnt;
 #pragma unroll
-    for (int k = 0; k < VT; ++k) {
-        if (bits & (1u << k)) {
-            out_idx[off] = first + k;
-            out_val[off] = acc[first + k];
-            acc[first + k] = 0.0;
-            ++off;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    const int64_t warp_off = __shfl_sync(0xffffffffu, off, 0);
+    const int64_t warp_first = first - (int64_t)lane * 64;
+    for (int c = 0; c < warp_total; c += 32) {
+        const int r = c + lane;
+        int owner = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int probe = __shfl_sync(0xffffffffu, incl, owner + step - 1);
+            if (probe <= r) owner += step;
+        }
+        owner = owner > 31 ? 31 : owner;
+        const int owner_excl = __shfl_sync(0xffffffffu, incl - cnt, owner);
+        const unsigned lo_bits = __shfl_sync(0xffffffffu, (unsigned)bits, owner);
+        const unsigned hi_bits = __shfl_sync(0xffffffffu, (unsigned)(bits >> 32), owner);
+        if (r < warp_total) {
+            const int j = r - owner_excl, nlo = __popc(lo_bits);
+            const int k = j < nlo ? (int)__fns(lo_bits, 0, j + 1) : 32 + (int)__fns(hi_bits, 0, j - nlo + 1);
+            const int64_t cell = warp_first + (int64_t)owner * 64 + k;
+            out_idx[warp_off + r] = cell;
+            out_val[warp_off + r] = acc[cell];
+            acc[cell] = 0.0;
         }
     }
 }
@@ -466,10 +493,11 @@ extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val
         rk.in_div[ax] = make_fastdiv((uint64_t)in_strides[ax]);
         rk.out_mul[ax] = out_strides[ax];
     }
-    // accumulators (cells doubles) then flags (cells bytes) in the workspace's self-cleaning slab
+    // accumulators (cells doubles) then one flag byte per cell (padded to 64) in the workspace's self-cleaning slab
     const size_t acc_bytes = ((size_t)cells * sizeof(double) + 255) & ~(size_t)255;
+    const int64_t nflags = ceil_div(cells, 64) * 64;
     {
-        const int rc0 = workspace_reserve_accum(ws, acc_bytes + (size_t)cells, stream);
+        const int rc0 = workspace_reserve_accum(ws, acc_bytes + (size_t)nflags, stream);
         if (rc0) return rc0;
     }
     double* const acc = reinterpret_cast<double*>(ws->accum);
@@ -493,7 +521,7 @@ extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val
 #undef SPB_ACC
     SPB_LAUNCHED(1);
     SPB_CUDA_TRY(cudaGetLastError());
-    const int64_t ntiles = ceil_div(cells, 256 * 16);
+    const int64_t ntiles = ceil_div(nflags, 256 * 64);
     if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
     int rc = workspace_reserve(ws, (size_t)ntiles * 8, stream);
     if (rc) return rc;
