@@ -113,12 +113,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)),
-        "r"(phase)
+        "r"(phase), "r"(0x989680u)     // suspend-time hint: sleep in hardware instead of re-issuing the poll
         : "memory");
 }
 
