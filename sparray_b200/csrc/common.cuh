@@ -347,10 +347,15 @@ __device__ __forceinline__ uint64_t lookback_exclusive_block256(const uint64_t* 
 // Block-wide (256 threads) exclusive scan of a per-thread count + decoupled look-back over
 // tiles: returns the global output offset of this thread's first emitted element.  The last
 // tile stores the grand total to *out_count.  Must be called by all 256 threads of the block.
+// WIDE: the whole block looks back (256 predecessors per round) -- for kernels whose tiles all run
+// in one or two waves and publish their counts at about the same moment, where the warp-wide walk
+// would need ntiles/32 dependent round trips for the last tile.
+template <bool WIDE = false>
 __device__ __forceinline__ int64_t compact_offset_256(int cnt, uint64_t* state, uint32_t epoch, int64_t tile,
                                                       bool last_tile, int64_t* out_count) {
     __shared__ int cs_warp[8];
     __shared__ int64_t cs_base;
+    __shared__ __align__(16) int cs_scratch[24];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int incl = cnt;
 #pragma unroll
@@ -361,7 +366,8 @@ __device__ __forceinline__ int64_t compact_offset_256(int cnt, uint64_t* state, 
     __syncthreads();            // protect cs_* against a previous call in the same kernel
     if (lane == 31) cs_warp[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
+    int tile_total = 0;
+    if (warp == 0 || WIDE) {
         int w = lane < 8 ? cs_warp[lane] : 0;
         int wi = w;
 #pragma unroll
@@ -369,8 +375,25 @@ __device__ __forceinline__ int64_t compact_offset_256(int cnt, uint64_t* state, 
             int t = __shfl_up_sync(0xffffffffu, wi, o);
             if (lane >= o) wi += t;
         }
-        if (lane < 8) cs_warp[lane] = wi - w;
-        const int tile_total = __shfl_sync(0xffffffffu, wi, 7);
+        tile_total = __shfl_sync(0xffffffffu, wi, 7);
+        if constexpr (WIDE) {
+            __syncthreads();    // every warp has read the per-warp totals
+        }
+        if (warp == 0 && lane < 8) cs_warp[lane] = wi - w;
+    }
+    if constexpr (WIDE) {
+        if (threadIdx.x == 0)
+            st_state(state + tile, pack_state(tile == 0 ? kStPrefix : kStAgg, epoch, (uint64_t)tile_total));
+        uint64_t base = 0;
+        if (tile > 0) {
+            base = lookback_exclusive_block256(state, tile, epoch, cs_scratch);
+            if (threadIdx.x == 0) st_state(state + tile, pack_state(kStPrefix, epoch, base + (uint64_t)tile_total));
+        }
+        if (threadIdx.x == 0) {
+            cs_base = (int64_t)base;
+            if (last_tile) *out_count = (int64_t)base + tile_total;
+        }
+    } else if (warp == 0) {
         uint64_t base = 0;
         if (tile == 0) {
             if (lane == 0) st_state(state, pack_state(kStPrefix, epoch, (uint64_t)tile_total));

@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict_
         }
     }
     const int cnt = __popcll(bits);
-    const int64_t off = compact_offset_256(cnt, state, epoch, tile, tile == gridDim.x - 1, out_count);
+    const int64_t off = compact_offset_256<true>(cnt, state, epoch, tile, tile == gridDim.x - 1, out_count);
     // Warp-cooperative emission: the warp's outputs are one contiguous run, written 32 at a time (coalesced
     // whether the cells are nearly all touched or nearly all empty).  Output r of the warp belongs to the
     // first lane whose inclusive count exceeds r, and is that lane's (r - exclusive count)-th set bit.
