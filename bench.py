@@ -7,7 +7,9 @@ each, 256 MB of operands: larger than L2, so nothing is re-used between steps) -
 ``c = a * b`` (intersection merge, flat.py:424-434) followed by ``c.sum(axis=2)``
 (flat.py:607-626).  metric = binop-merge throughput in input nnz per second.
 
-  value      : whole-job Gnnz/s with operands resident in HBM (CUDA events, max over ranks)
+  value      : whole-job Gnnz/s with operands resident in HBM (CUDA events, max over ranks); steps are
+               enqueued back to back -- results keep their element counts on the device (lazily
+               counted FlatSparray results), the last step's result is resolved inside the timed region
   e2e        : same metric through the public FlatSparray API starting from pinned HOST
                buffers (H2D of all four operand arrays and D2H of the result inside the
                timed region)
@@ -41,9 +43,9 @@ DTYPE = np.float32
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # ncu --set full capture of this workload (profiles/README.md); None until a capture exists
-NCU_TRAFFIC_BYTES = 201036544   # 196.18 MB read + 4.86 MB written
+NCU_TRAFFIC_BYTES = 200181504   # 195.63 MB read + 4.55 MB written
 NCU_TRAFFIC_SOURCE = ("profiles/r1_setop_intersect_final_ncu_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum of "
-                      "setop_kernel<float,float,INTERSECT> (73 % of the call's GPU time; the partition and reorder "
+                      "setop_kernel<float,float,INTERSECT> (74 % of the call's GPU time; the partition and reorder "
                       "launches were not captured with --set full)")
 
 
@@ -399,7 +401,9 @@ def synth_sorted(torch, n, size, dtype, seed):
 
 
 def op_breakdown(sp, torch, A, B, peak):
-    """API-level timings (count read-back included) at the other BASELINE configs."""
+    """API-level timings at the other BASELINE configs (CUDA events around the call; binops and dense
+    axis sums return lazily counted results, so their count read-back is not inside; the sort-based
+    ops, last-axis sums and SpMV synchronise as part of the call)."""
     res = {}
 
     def rec(name, n_in, alg_bytes, fn, reps=10):
