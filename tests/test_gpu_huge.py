@@ -1,0 +1,74 @@
+"""Beyond-int32 sizes on one GPU (opt-in: SPB_RUN_HUGE=1; needs ~100 GB of HBM and a minute).
+
+BASELINE config 5 is 2.1e9 stored elements per operand, sharded over 8 GPUs; this test pushes a
+single shard PAST 2^31 elements so that every 64-bit offset in the partition search, the tile
+descriptors, the slot reservation, the reorder pass and the segmented reduce is exercised.  No CPU
+oracle can hold these arrays, so parity is established through constructions with a known answer:
+b is every other element of a, hence  a & b == b  (with known positions) and  a | b == a."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HUGE = os.environ.get("SPB_RUN_HUGE") == "1"
+
+
+@pytest.mark.skipif(not HUGE, reason="opt-in (SPB_RUN_HUGE=1): allocates ~100 GB of HBM")
+def test_past_int32_elements():
+    import torch
+    import sparray_b200 as sp
+    from sparray_b200 import _kernels as k
+    n = (1 << 31) + (1 << 27) + 12345            # 2.28e9 elements in a
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    a = torch.randint(1, 4, (n,), device="cuda", generator=g, dtype=torch.int64)
+    torch.cumsum(a, 0, out=a)                    # sorted, duplicate-free, < 3n
+    b = a[::2].contiguous()
+    na, nb = a.numel(), b.numel()
+    assert na > 2 ** 31
+
+    def val_of(idx, m):
+        return (idx % m).to(torch.float32)
+    av, bv = val_of(a, 7), val_of(b, 5)
+
+    # ---- intersection with values: a * b lives on b's pattern -----------------------------------
+    idx, val, cnt = k.setop_binop("intersect", "mul", a, av, b, bv, lazy=True)
+    assert int(cnt.item()) == nb
+    assert bool((idx[:nb] == b).all().item())
+    want = val_of(b, 7)
+    want *= bv
+    assert bool((val[:nb] == want).all().item())
+    del idx, val, want
+    torch.cuda.empty_cache()
+
+    # ---- the seam form: positions ----------------------------------------------------------------
+    out, ia, ib = k.intersect1d_sorted(a, b, return_inds=True)
+    assert out.numel() == nb and bool((out == b).all().item())
+    assert bool((ib == torch.arange(nb, device="cuda")).all().item())
+    assert bool((ia == 2 * ib).all().item())
+    del out, ia, ib
+    torch.cuda.empty_cache()
+
+    # ---- union with values: a + b lives on a's pattern ----------------------------------------------
+    idx, val, cnt = k.setop_binop("union", "add", a, av, b, bv, lazy=True)
+    assert int(cnt.item()) == na
+    assert bool((idx[:na] == a).all().item())
+    want = av.clone()
+    want[::2] += bv
+    assert bool((val[:na] == want).all().item())
+    del idx, val, want
+    torch.cuda.empty_cache()
+
+    # ---- last-axis sum over > 2^31 elements: totals are exact (small integers in float64) ---------------
+    ncols = 64
+    nrows = int(a[-1].item()) // ncols + 1
+    A = sp.FlatSparray(a, av, shape=(nrows, ncols), is_canonical=True)
+    s = A.sum(axis=1)
+    assert float(s.data.sum().item()) == float(av.sum(dtype=torch.float64).item())
+    rows = a // ncols                            # (torch's own unique/select kernels refuse > 2^31 inputs)
+    n_rows = int((rows[1:] != rows[:-1]).sum().item()) + 1
+    assert s.nnz == n_rows
+    assert bool((s.indices[1:] > s.indices[:-1]).all().item())
+    assert int(s.indices[0].item()) == int(rows[0].item()) and int(s.indices[-1].item()) == int(rows[-1].item())
