@@ -1,5 +1,5 @@
-"""Event-timed API-level medians of the non-merge ops on config-shaped operands (used with
-SPB_DEBUG for elimination timing).  Usage: python profiles/time_ops.py"""
+"""Event-timed API-level medians of the non-merge ops on config-shaped operands.
+Usage: python profiles/time_ops.py"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -19,7 +19,6 @@ def t(fn, reps=10):
 shape = (256, 256, 256, 64)
 ai, av = synth(10_700_000, 256 * 256 * 256 * 64, torch.float32, 1)
 A = sp.FlatSparray(ai, av, shape=shape, is_canonical=True)
-print("SPB_DEBUG=%s" % os.environ.get("SPB_DEBUG", "0"))
 print("sum_axis3 (last) f32 10.7M: %.0f us" % t(lambda: A.sum(axis=3)))
 print("sum_axis2 f32 10.7M: %.0f us" % t(lambda: A.sum(axis=2)))
 print("transpose 3210 f32 10.7M: %.0f us" % t(lambda: A.transpose(3, 2, 1, 0)))

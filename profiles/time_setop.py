@@ -1,5 +1,5 @@
-"""Kernel-only timing of the fused setop kernels (CUDA events), optionally under SPB_DEBUG
-elimination flags.  Usage: python profiles/time_setop.py"""
+"""Kernel-only timing of the fused setop calls (CUDA events around the C-ABI call, config-2
+operands).  Usage: python profiles/time_setop.py"""
 import os, sys
 import numpy as np
 import torch
@@ -30,7 +30,7 @@ def main():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); launch(); b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
-        print("SPB_DEBUG=%s %s: median %.1f us  min %.1f us  (nout=%d)" % (os.environ.get("SPB_DEBUG", "0"), name,
+        print("%s: median %.1f us  min %.1f us  (nout=%d)" % (name,
               np.median(ts) * 1e3, np.min(ts) * 1e3, int(cnt.item())))
 
 if __name__ == "__main__":

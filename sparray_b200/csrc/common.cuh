@@ -131,11 +131,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
         : "memory");
 }
 
-// order generic-proxy shared-memory accesses before later async-proxy (TMA) writes
-__device__ __forceinline__ void fence_proxy_async_smem() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
 // Plan for staging global elements [g_lo, g_hi) of an array with element size E
 // (E divides 16) into a 16-byte aligned shared buffer.  Element i of the global
 // array lands at byte offset (base + i*E) - align_down(base + g_lo*E, 16) from
@@ -239,71 +234,9 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* state, in
     return total;
 }
 
-// Warp variant that inspects W predecessor tiles per lane (32 W per round, all loads in flight
-// at once).  It only ever waits for tiles NEARER than the nearest inclusive prefix it can see:
-// words farther back are ignored even if they are not published yet.
-template <int W = 8>
-__device__ __forceinline__ uint64_t lookback_exclusive_wide(const uint64_t* state, int64_t tile, uint32_t epoch) {
-    const int lane = threadIdx.x & 31;
-    uint64_t total = 0;
-    int64_t base = tile - 1;
-    while (base >= 0) {
-        uint64_t w[W];
-#pragma unroll
-        for (int j = 0; j < W; ++j) {
-            const int64_t t = base - (lane * W + j);
-            w[j] = t >= 0 ? ld_state(state + t) : pack_state(kStPrefix, epoch, 0);
-        }
-        uint64_t part;
-        bool found;      // this lane reached a prefix with every nearer word of its own valid
-        bool clean;      // every word of this lane is valid
-        for (;;) {
-            part = 0;
-            found = false;
-            clean = true;
-#pragma unroll
-            for (int j = 0; j < W; ++j) {
-                const bool valid = (w[j] >> 62) != 0 && (uint32_t)((w[j] >> 48) & ((1u << kEpochBits) - 1)) == epoch;
-                if (clean && !found) {
-                    if (!valid) clean = false;
-                    else {
-                        part += w[j] & kCountMask;
-                        found = (w[j] >> 62) == kStPrefix;
-                    }
-                }
-            }
-            // nearest lane that reached a prefix; all nearer lanes must be fully valid
-            const unsigned fm = __ballot_sync(0xffffffffu, found);
-            const unsigned dirty = __ballot_sync(0xffffffffu, !clean && !found);
-            const int stop = fm ? (__ffs(fm) - 1) : 32;
-            const unsigned need = stop >= 32 ? 0xffffffffu : ((1u << stop) - 1u);
-            if ((dirty & need) == 0 && (fm || dirty == 0)) break;
-            // somebody nearer than the prefix is not published yet: poll those words again
-            if (!clean && !found && (lane < stop)) {
-                __nanosleep(40);
-#pragma unroll
-                for (int j = 0; j < W; ++j) {
-                    const int64_t t = base - (lane * W + j);
-                    const bool valid = (w[j] >> 62) != 0 && (uint32_t)((w[j] >> 48) & ((1u << kEpochBits) - 1)) == epoch;
-                    if (!valid && t >= 0) w[j] = ld_state(state + t);
-                }
-            }
-        }
-        const unsigned has_prefix = __ballot_sync(0xffffffffu, found);
-        const int stop = has_prefix ? (__ffs(has_prefix) - 1) : 31;
-        uint64_t v = lane <= stop ? part : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        total += v;
-        if (has_prefix) break;
-        base -= 32 * W;
-    }
-    return total;
-}
-
 // Block-wide variant for 256-thread CTAs: every thread inspects one predecessor tile, so a
 // whole wave of concurrently running tiles (persistent kernels: a few hundred) is covered in one
-// or two rounds instead of a dozen dependent warp-wide ones.  `scratch` = 20 ints of shared
+// or two rounds instead of a dozen dependent warp-wide ones.  `scratch` = 24 ints (16-byte aligned) of shared
 // memory.  Must be called by all 256 threads; returns the exclusive prefix in every thread.
 __device__ __forceinline__ uint64_t lookback_exclusive_block256(const uint64_t* state, int64_t tile, uint32_t epoch,
                                                                 int* scratch) {
@@ -411,48 +344,7 @@ __device__ __forceinline__ int64_t compact_offset_256(int cnt, uint64_t* state, 
     return cs_base + cs_warp[warp] + incl - cnt;
 }
 
-// ---------------------------------------------------------------------------
-// Merge-path split of diagonal d over two sorted global arrays, ties to A.
-// Returns i = number of A elements among the first d merged elements.
-// Called by one full warp (32-ary search: ~log32(range) dependent round trips).
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ int64_t merge_path_warp(const int64_t* __restrict__ a, int64_t na,
-                                                   const int64_t* __restrict__ b, int64_t nb, int64_t d) {
-    const int lane = threadIdx.x & 31;
-    int64_t lo = d > nb ? d - nb : 0;
-    int64_t hi = d < na ? d : na;
-    while (lo < hi) {
-        int64_t span = hi - lo;
-        // probes m_0 = lo <= m_1 <= ... <= m_31 < hi
-        int64_t m = lo + (int64_t)(((unsigned __int128)span * (unsigned)lane) >> 5);
-        bool take_a = __ldg(a + m) <= __ldg(b + (d - 1 - m));       // predicate true => answer > m
-        unsigned bal = __ballot_sync(0xffffffffu, take_a);
-        int c = __popc(bal);                                        // monotone: trues occupy low lanes
-        if (c == 0) {
-            hi = lo;
-            break;
-        }
-        int64_t m_last_true = __shfl_sync(0xffffffffu, m, c - 1);
-        int64_t m_first_false = __shfl_sync(0xffffffffu, m, c < 32 ? c : 31);
-        lo = m_last_true + 1;
-        if (c < 32) hi = m_first_false;
-    }
-    return lo;
-}
 
-// Serial version over shared (or any) memory, one thread.
-__device__ __forceinline__ int merge_path_thread(const int64_t* a, int na, const int64_t* b, int nb, int d) {
-    int lo = d > nb ? d - nb : 0;
-    int hi = d < na ? d : na;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (a[mid] <= b[d - 1 - mid])
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    return lo;
-}
 
 // ---------------------------------------------------------------------------
 // Exact floor(n / d) for 0 <= n < 2^63, 1 <= d < 2^63, d fixed per launch.

@@ -8,29 +8,31 @@
 //     (_merge.pyx:87-88) + the gathers of _pairwise_sparray_fixed_zero
 //     (flat.py:429-433)                                           -> intersection kernels
 //
-// Two launches per call:
-//   1. merge_partition_kernel: one warp per tile boundary finds the merge-path split of
-//      its diagonal on the two global arrays (32-ary cooperative search, ~5 round trips).
-//   2. setop_kernel: persistent CTAs (a few per SM) walk the tiles in stride.  Per tile
-//        - warp 0 PREFETCHES the next tile while the current one is merged: TMA bulk
-//          copies (cp.async.bulk + mbarrier) of the A / B index ranges and value ranges
-//          into the other shared-memory buffer; the < 16-byte unaligned heads / tails
-//          and the halo keys ride in registers of that warp until the buffer is used;
-//        - the staged 64-bit keys are re-based to 32-bit tile-local offsets whenever the
-//          tile's key span allows it (64-bit path otherwise), so the merge runs on
-//          single-register keys;
-//        - every thread merge-path-splits the tile in shared memory and walks kVT items
-//          with a branch-free step that only records three bit masks (took-A, matched,
-//          emitted); a key present in both inputs is emitted once, by its A element
-//          (the B partner is found through the halo key even across a tile boundary);
-//        - block scan of the output counts, decoupled look-back across tiles, then the
-//          emitted items are materialised (value op applied; for intersections the two
-//          values are gathered straight from global memory, so unmatched values are
-//          never read), compacted through shared memory and stored coalesced.
+// Launches per call (chained with programmatic dependent launch):
+//   1. merge_partition_kernel: a half-warp per tile boundary finds the merge-path split of its
+//      diagonal on the two global arrays (bracketed around the proportional guess, then 16-ary);
+//      one thread per tile turns two neighbouring splits into a 128-byte staging descriptor.
+//   2. setop_kernel: ONE tile per CTA, in blockIdx order; 6 (intersections) or 3-4 (unions) CTAs per
+//      SM hide each other's latencies.  Per tile
+//        - the staging warp loads the descriptor and issues TMA bulk copies (cp.async.bulk +
+//          mbarrier) of the A / B index ranges (unions: and the value ranges); the < 16-byte
+//          unaligned heads / tails and the halo keys ride in registers of that warp;
+//        - the staged 64-bit keys are read as 32-bit tile-local offsets whenever the tile's key
+//          span allows it (64-bit path otherwise), so the merge runs on single-register keys;
+//        - every thread merge-path-splits the tile in shared memory and walks kVT items with a
+//          branch-free step that only records three bit masks (took-A, matched, emitted); a key
+//          present in both inputs is emitted once, by its A element (the B partner is found
+//          through the halo key even across a tile boundary);
+//        - block scan of the output counts; then
+//          unions: a helper warp has been resolving the tile's output offset by decoupled
+//          look-back since the tile was staged; items are materialised into a shared staging area
+//          (value op applied) and stored coalesced;
+//          intersections: no look-back -- the tile owns private output slots (one atomic only if
+//          it overflows them), only the set bits of the match mask are visited, the two values of
+//          a match are gathered straight from global memory (unmatched values are never read).
+//   3. merge_reorder_kernel (intersections): chunks into tile order, writes the count.
 //      No lut / mask array ever exists and nothing is read twice.
 #include "common.cuh"
-
-#include <stdlib.h>
 
 namespace spb {
 
@@ -112,7 +114,6 @@ struct SetopParams {
     void* tmp_val;
     int64_t* tmp_apos;
     int64_t* tmp_bpos;
-    int debug;           // SPB_DEBUG experiments (timing only; results are wrong when set)
     int negate_b;        // a - b is evaluated as a + (-b), base.py:45-46: a missing partner is +0, not -0
 };
 
@@ -436,8 +437,8 @@ __device__ __forceinline__ void sync_mergers() {
 }
 
 // One CTA = one tile (blockIdx order, so the decoupled look-back only ever waits on tiles that
-// started earlier).  Latency is hidden across the 3-4 CTAs resident per SM: while one waits for
-// its TMA copies, others merge or store.
+// started earlier).  Latency is hidden across the CTAs resident per SM (6 for intersections, 3-4 for
+// unions): while one waits for its TMA copies, others merge or store.
 template <typename V, typename VO, int KIND, bool HAS_VAL, bool SEAM>
 __global__ void __launch_bounds__(Cfg<V, VO, KIND, HAS_VAL, SEAM>::kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMinCtas)
 setop_kernel(const SetopParams p) {
@@ -500,7 +501,7 @@ setop_kernel(const SetopParams p) {
             // The exclusive prefix of the EARLIER tiles does not depend on this tile's own count, so the
             // look-back starts now and overlaps the TMA flight and the whole merge.
             uint64_t b = 0;
-            if (tile > 0 && !(p.debug & 1)) b = lookback_exclusive(p.state, tile, p.epoch);
+            if (tile > 0) b = lookback_exclusive(p.state, tile, p.epoch);
             mbar_wait(agg_bar, 0);                                     // the mergers have published the count
             const int total = *tot_s;
             if (lane == 0) {
@@ -541,9 +542,7 @@ setop_kernel(const SetopParams p) {
     const int steps = (items - diag) < kVT ? (items - diag) : kVT;
     int ai0, bi0;
     unsigned m_ta, m_eq, m_emit;
-    if (p.debug & 2) {
-        ai0 = diag / 2; bi0 = diag - ai0; m_ta = 0x55; m_eq = 0; m_emit = KIND == KIND_UNION ? 0xff : 0;
-    } else if (narrow) {
+    if (narrow) {
         const NarrowKeys A{reinterpret_cast<const uint32_t*>(As64), (uint32_t)kbase};
         const NarrowKeys B{reinterpret_cast<const uint32_t*>(Bs64), (uint32_t)kbase};
         ai0 = merge_path_smem(A, an, B, bn, diag);
@@ -675,7 +674,7 @@ setop_kernel(const SetopParams p) {
     mbar_wait(ready_bar, 0);                                           // offset resolved by the helper warp
     const int64_t base = *base_s;
     VO* const o_val = reinterpret_cast<VO*>(p.out_val);
-    for (int i = tid < kNT ? tid : tile_total; i < ((p.debug & 4) ? 0 : tile_total); i += kNT) {
+    for (int i = tid < kNT ? tid : tile_total; i < tile_total; i += kNT) {
         p.out_idx[base + i] = skey[i];
         if constexpr (HAS_VAL) o_val[base + i] = sval[i];
         if constexpr (SEAM && KIND == KIND_UNION) {
@@ -758,10 +757,6 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     if (rc) return rc;
     p.state = ws_state(ws);
     p.ntiles = ntiles;
-    {
-        const char* dbg = getenv("SPB_DEBUG");
-        p.debug = dbg ? atoi(dbg) : 0;
-    }
     p.desc = reinterpret_cast<uint64_t*>(ws->payload);
     auto kern = setop_kernel<V, VO, KIND, HAS_VAL, SEAM>;
     static int ctas_per_sm = 0;
