@@ -72,3 +72,32 @@ def test_past_int32_elements():
     assert s.nnz == n_rows
     assert bool((s.indices[1:] > s.indices[:-1]).all().item())
     assert int(s.indices[0].item()) == int(rows[0].item()) and int(s.indices[-1].item()) == int(rows[-1].item())
+
+
+@pytest.mark.skipif(not HUGE, reason="opt-in (SPB_RUN_HUGE=1): allocates ~110 GB of HBM")
+def test_config3_stated_size_swapaxes_round_trip():
+    """BASELINE config 3 at its stated size: (4096,4096,1024) float32 with 1.7e9 stored elements;
+    swapaxes(0,2) there and back is the identity, the middle state is sorted and holds the same values."""
+    import torch
+    import sparray_b200 as sp
+    shape = (4096, 4096, 1024)
+    n = 1_717_986_918
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    idx = torch.randint(1, 20, (n,), device="cuda", generator=g, dtype=torch.int64)
+    torch.cumsum(idx, 0, out=idx)
+    idx = idx[idx < 2 ** 34].contiguous()
+    val = (idx % 251).to(torch.float32)
+    Z = sp.FlatSparray(idx, val, shape=shape, is_canonical=True)
+    T = Z.swapaxes(0, 2)
+    assert T.shape == (1024, 4096, 4096) and T.nnz == Z.nnz
+    assert bool((T.indices[1:] > T.indices[:-1]).all().item())
+    # element (i, j, k) of Z sits at (k, j, i) of T: recompute the old key from the new one
+    ti = T.indices
+    old = (ti % 4096) * (4096 * 1024) + ((ti // 4096) % 4096) * 1024 + ti // (4096 * 4096)
+    assert bool((T.data == (old % 251).to(torch.float32)).all().item())
+    del old, ti
+    torch.cuda.empty_cache()
+    B = T.swapaxes(0, 2)
+    del T
+    assert bool((B.indices == idx).all().item()) and bool((B.data == val).all().item())
