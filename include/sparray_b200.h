@@ -227,6 +227,18 @@ int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val, int64_t n
                        int64_t cells, int64_t* out_idx, double* out_sums, int64_t* out_count,
                        spb_workspace* ws, spb_stream_t stream);
 
+/* The two halves of spb_axis_sum_dense on caller-owned buffers, for the sharded axis sum of
+ * SURVEY.md section 8(e) (dense per-GPU accumulators + all-reduce): acc = cells doubles,
+ * touched = cells flag bytes padded to a multiple of 64 and 16-byte aligned, both zeroed by the
+ * caller.  spb_emit_touched emits the touched cells of [cell_lo, cell_hi) in key order (absolute cell
+ * numbers; cell_lo a multiple of 64; out_idx / out_sums: cell_hi - cell_lo slots) and zeroes them. */
+int spb_axis_accumulate(int dtype, const int64_t* idx, const void* val, int64_t n,
+                        int ndim, const int64_t* in_strides_host, const int64_t* out_strides_host,
+                        int64_t cells, double* acc, uint8_t* touched, spb_stream_t stream);
+int spb_emit_touched(double* acc, uint8_t* touched, int64_t cell_lo, int64_t cell_hi,
+                     int64_t* out_idx, double* out_sums, int64_t* out_count,
+                     spb_workspace* ws, spb_stream_t stream);
+
 /* ---- 6. __getitem__: flat.py:254-325, 366-393 ---------------------------------- */
 
 /* ints + slices (flat.py:270-274) without materialising the box: keeps the stored

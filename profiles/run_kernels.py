@@ -1,7 +1,7 @@
 """Small driver used for ncu captures: launches each hot kernel a few times on
 config-shaped synthetic operands through the C ABI (no timing here; numbers taken
 under a profiler are never bench values).  Usage: python profiles/run_kernels.py [op ...]
-ops: intersect union sum_last sum_mid transpose spmv"""
+ops: intersect union sum_last sum_mid transpose spmv sum_c4"""
 import os
 import sys
 
@@ -47,6 +47,11 @@ def main():
         x = torch.randn(10 ** 6, device="cuda", dtype=torch.float64)
         for _ in range(reps):
             k.spmv(wi, wv, 10 ** 6, 10 ** 6, x, torch.float64)
+    if "sum_c4" in ops:
+        wi, wv = synth(100_000_000, 10 ** 12, torch.float64, 4)
+        W = sp.FlatSparray(wi, wv, shape=(10 ** 6, 10 ** 6), is_canonical=True)
+        for _ in range(reps):
+            W.sum(axis=1)
     torch.cuda.synchronize()
     print("done")
 

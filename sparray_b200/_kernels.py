@@ -332,6 +332,38 @@ def axis_sum_dense(idx, val, in_strides, out_strides, cells, n_dev=None):
     return out_idx, out_sums, cnt
 
 
+def axis_accumulate(idx, val, in_strides, out_strides, cells):
+    """Local half of a sharded dense axis sum: (float64 accumulators [cells], flag bytes [cells padded
+    to 64]) holding this shard's contributions; to be all-reduced (SUM / MAX) across ranks."""
+    require_cuda()
+    cells = int(cells)
+    acc = torch.zeros(cells, dtype=torch.float64, device=idx.device)
+    touched = torch.zeros((cells + 63) // 64 * 64, dtype=torch.uint8, device=idx.device)
+    ndim = len(in_strides)
+    ins = (ctypes.c_int64 * ndim)(*in_strides)
+    outs = (ctypes.c_int64 * ndim)(*out_strides)
+    check(lib.spb_axis_accumulate(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), idx.numel(), ndim,
+                                  ctypes.cast(ins, ctypes.c_void_p), ctypes.cast(outs, ctypes.c_void_p), cells,
+                                  ptr(acc), ptr(touched), stream()))
+    return acc, touched
+
+
+def emit_touched(acc, touched, lo, hi):
+    """Touched cells of [lo, hi) as (sorted absolute cell numbers, float64 sums); lo % 64 == 0."""
+    require_cuda()
+    lo, hi = int(lo), int(hi)
+    if hi <= lo:
+        return (torch.empty(0, dtype=torch.int64, device=acc.device),
+                torch.empty(0, dtype=torch.float64, device=acc.device))
+    out_idx = torch.empty(hi - lo, dtype=torch.int64, device=acc.device)
+    out_sums = torch.empty(hi - lo, dtype=torch.float64, device=acc.device)
+    cnt = torch.empty(1, dtype=torch.int64, device=acc.device)
+    check(lib.spb_emit_touched(ptr(acc), ptr(touched), lo, hi, ptr(out_idx), ptr(out_sums), ptr(cnt), workspace(),
+                               stream()))
+    k = _count(cnt)
+    return _trim(out_idx, k), _trim(out_sums, k)
+
+
 def canonicalize(idx, val, max_key=None):
     """Sort by index and sum duplicates in float64, cast back (flat.py:32-35)."""
     if idx.numel() == 0:

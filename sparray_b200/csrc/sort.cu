@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
 // 64 cells (four 16-byte loads of flag bytes); a tile of 256 threads covers 16 K cells, which keeps
 // the look-back chain short.
 __global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict__ acc, uint8_t* __restrict__ touched,
-                                                             int64_t cells, int64_t* __restrict__ out_idx,
+                                                             int64_t cells, int64_t key_base, int64_t* __restrict__ out_idx,
                                                              double* __restrict__ out_val, int64_t* out_count,
                                                              uint64_t* state, uint32_t epoch) {
     const int64_t tile = blockIdx.x;
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict_
             const int j = r - owner_excl, nlo = __popc(lo_bits);
             const int k = j < nlo ? (int)__fns(lo_bits, 0, j + 1) : 32 + (int)__fns(hi_bits, 0, j - nlo + 1);
             const int64_t cell = warp_first + (int64_t)owner * 64 + k;
-            out_idx[warp_off + r] = cell;
+            out_idx[warp_off + r] = key_base + cell;
             out_val[warp_off + r] = acc[cell];
             acc[cell] = 0.0;
         }
@@ -477,31 +477,21 @@ __global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict_
 
 }  // namespace spb
 
-extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev, int ndim,
-                                  const int64_t* in_strides, const int64_t* out_strides, int64_t cells,
-                                  int64_t* out_idx, double* out_sums, int64_t* out_count,
-                                  spb_workspace* ws, spb_stream_t stream) {
-    using namespace spb;
-    if (n < 0 || cells < 0 || ndim < 1 || ndim > kMaxRekeyDims || !in_strides || !out_strides || !out_count)
-        return SPB_ERR_BAD_ARG;
-    if (n == 0 || cells == 0) return (int)cudaMemsetAsync(out_count, 0, 8, stream);
-    if (!idx || !val || !out_idx || !out_sums || !ws) return SPB_ERR_BAD_ARG;
-    Rekey rk{};
+namespace spb {
+
+static int make_rekey(Rekey& rk, int ndim, const int64_t* in_strides, const int64_t* out_strides) {
+    if (ndim < 1 || ndim > kMaxRekeyDims || !in_strides || !out_strides) return SPB_ERR_BAD_ARG;
     rk.ndim = ndim;
     for (int ax = 0; ax < ndim; ++ax) {
         if (in_strides[ax] < 1 || out_strides[ax] < 0) return SPB_ERR_BAD_ARG;
         rk.in_div[ax] = make_fastdiv((uint64_t)in_strides[ax]);
         rk.out_mul[ax] = out_strides[ax];
     }
-    // accumulators (cells doubles) then one flag byte per cell (padded to 64) in the workspace's self-cleaning slab
-    const size_t acc_bytes = ((size_t)cells * sizeof(double) + 255) & ~(size_t)255;
-    const int64_t nflags = ceil_div(cells, 64) * 64;
-    {
-        const int rc0 = workspace_reserve_accum(ws, acc_bytes + (size_t)nflags, stream);
-        if (rc0) return rc0;
-    }
-    double* const acc = reinterpret_cast<double*>(ws->accum);
-    uint8_t* const touched = reinterpret_cast<uint8_t*>(ws->accum) + acc_bytes;
+    return SPB_OK;
+}
+
+static int launch_accumulate(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev,
+                             const Rekey& rk, double* acc, uint8_t* touched, cudaStream_t stream) {
     int64_t blocks = ceil_div(n, 256 * 4);
     if (blocks > 148 * 16) blocks = 148 * 16;
 #define SPB_ACC(T)                                                                                            \
@@ -520,8 +510,13 @@ extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val
     }
 #undef SPB_ACC
     SPB_LAUNCHED(1);
-    SPB_CUDA_TRY(cudaGetLastError());
-    const int64_t ntiles = ceil_div(nflags, 256 * 64);
+    return (int)cudaGetLastError();
+}
+
+// cells of [0, cells) relative to acc / touched (touched readable up to the next multiple of 64)
+static int launch_select(double* acc, uint8_t* touched, int64_t cells, int64_t key_base, int64_t* out_idx,
+                         double* out_sums, int64_t* out_count, spb_workspace* ws, cudaStream_t stream) {
+    const int64_t ntiles = ceil_div(cells, 256 * 64);
     if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
     int rc = workspace_reserve(ws, (size_t)ntiles * 8, stream);
     if (rc) return rc;
@@ -529,7 +524,62 @@ extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val
     rc = workspace_next_epoch(ws, stream, &epoch);
     if (rc) return rc;
     SPB_CUDA_TRY(launch_pdl(select_touched_kernel, dim3((unsigned)ntiles), dim3(256), 0, stream, acc, touched, cells,
-                            out_idx, out_sums, out_count, ws_state(ws), epoch));
+                            key_base, out_idx, out_sums, out_count, ws_state(ws), epoch));
     SPB_LAUNCHED(1);
     return (int)cudaGetLastError();
+}
+
+}  // namespace spb
+
+extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev, int ndim,
+                                  const int64_t* in_strides, const int64_t* out_strides, int64_t cells,
+                                  int64_t* out_idx, double* out_sums, int64_t* out_count,
+                                  spb_workspace* ws, spb_stream_t stream) {
+    using namespace spb;
+    if (n < 0 || cells < 0 || !out_count) return SPB_ERR_BAD_ARG;
+    Rekey rk{};
+    int rc = make_rekey(rk, ndim, in_strides, out_strides);
+    if (rc) return rc;
+    if (n == 0 || cells == 0) return (int)cudaMemsetAsync(out_count, 0, 8, stream);
+    if (!idx || !val || !out_idx || !out_sums || !ws) return SPB_ERR_BAD_ARG;
+    // accumulators (cells doubles) then one flag byte per cell (padded to 64) in the workspace's self-cleaning slab
+    const size_t acc_bytes = ((size_t)cells * sizeof(double) + 255) & ~(size_t)255;
+    const int64_t nflags = ceil_div(cells, 64) * 64;
+    rc = workspace_reserve_accum(ws, acc_bytes + (size_t)nflags, stream);
+    if (rc) return rc;
+    double* const acc = reinterpret_cast<double*>(ws->accum);
+    uint8_t* const touched = reinterpret_cast<uint8_t*>(ws->accum) + acc_bytes;
+    rc = launch_accumulate(dtype, idx, val, n, n_dev, rk, acc, touched, stream);
+    if (rc) return rc;
+    return launch_select(acc, touched, cells, 0, out_idx, out_sums, out_count, ws, stream);
+}
+
+// The two halves on caller-owned buffers, for the sharded axis sum (all-reduce of the accumulators
+// between them): acc = cells doubles, touched = cells flag bytes padded to a multiple of 64, both
+// zeroed by the caller, touched 16-byte aligned.
+extern "C" int spb_axis_accumulate(int dtype, const int64_t* idx, const void* val, int64_t n, int ndim,
+                                   const int64_t* in_strides, const int64_t* out_strides, int64_t cells, double* acc,
+                                   uint8_t* touched, spb_stream_t stream) {
+    using namespace spb;
+    if (n < 0 || cells < 0) return SPB_ERR_BAD_ARG;
+    Rekey rk{};
+    const int rc = make_rekey(rk, ndim, in_strides, out_strides);
+    if (rc) return rc;
+    if (n == 0 || cells == 0) return SPB_OK;
+    if (!idx || !val || !acc || !touched) return SPB_ERR_BAD_ARG;
+    return launch_accumulate(dtype, idx, val, n, nullptr, rk, acc, touched, stream);
+}
+
+// Emit the touched cells of [cell_lo, cell_hi) in key order (keys are absolute cell numbers).
+// cell_lo must be a multiple of 64 (flag words are read 16 bytes at a time); the cells that are
+// emitted are zeroed.  out_idx / out_sums: cell_hi - cell_lo slots.
+extern "C" int spb_emit_touched(double* acc, uint8_t* touched, int64_t cell_lo, int64_t cell_hi, int64_t* out_idx,
+                                double* out_sums, int64_t* out_count, spb_workspace* ws, spb_stream_t stream) {
+    using namespace spb;
+    if (cell_lo < 0 || cell_hi < cell_lo || (cell_lo & 63) != 0 || !out_count) return SPB_ERR_BAD_ARG;
+    if (cell_hi == cell_lo) return (int)cudaMemsetAsync(out_count, 0, 8, stream);
+    if (!acc || !touched || !out_idx || !out_sums || !ws) return SPB_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(touched) & 15) != 0) return SPB_ERR_BAD_ARG;
+    return launch_select(acc + cell_lo, touched + cell_lo, cell_hi - cell_lo, cell_lo, out_idx, out_sums, out_count, ws,
+                         stream);
 }

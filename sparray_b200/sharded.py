@@ -54,11 +54,20 @@ class CudaOps:
     def rekey_sort(self, idx, val, in_s, out_s, div, bits):
         return self.k.rekey_sort(idx, val, in_s, out_s, div, bits)
 
+    def axis_accumulate(self, idx, val, in_s, out_s, cells):
+        return self.k.axis_accumulate(idx, val, in_s, out_s, cells)
+
+    def emit_touched(self, acc, touched, lo, hi):
+        return self.k.emit_touched(acc, touched, lo, hi)
+
     def spmv(self, idx, val, ncols, nrows, x):
         return self.k.spmv(idx, val, ncols, nrows, x, val.dtype)
 
     def device(self):
         return torch.device("cuda", torch.cuda.current_device())
+
+
+DENSE_ALLREDUCE_MAX_CELLS = 1 << 24      # 128 MiB of float64 accumulators per GPU
 
 
 def _size(shape):
@@ -190,8 +199,21 @@ class ShardedFlatSparray:
             keys, sums = self.ops.reduce_by_key(self.indices, self.data, div)
             new_split = [s // div for s in self.splitters[:-1]] + [_size(new_shape)]
             return self._fix_borders(keys, sums, new_shape, new_split)
-        # middle axis: local re-key + sort + reduce, then exchange partial sums by output-key range
         _, in_s, out_s, bits = plan
+        cells = _size(new_shape)
+        if cells <= DENSE_ALLREDUCE_MAX_CELLS:
+            # reduced array small enough to hold densely on every GPU: local float64
+            # accumulators, one all-reduce of the sums and one of the "touched" flags, then every rank
+            # emits its own range of output cells (ranges aligned to 64 cells)
+            acc, touched = self.ops.axis_accumulate(self.indices, self.data, in_s, out_s, cells)
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(touched, op=dist.ReduceOp.MAX, group=self.group)
+            per = -(-cells // self.world)
+            per = -(-per // 64) * 64
+            out_split = [min(r * per, cells) for r in range(self.world)] + [cells]
+            keys, sums = self.ops.emit_touched(acc, touched, out_split[self.rank], out_split[self.rank + 1])
+            return ShardedFlatSparray(keys, sums, new_shape, out_split, self.group, self.ops)
+        # middle axis, large output: local re-key + sort + reduce, then exchange partial sums by output-key range
         keys, vals = self.ops.rekey_sort(self.indices, self.data, in_s, out_s, 1, bits)
         keys, sums = self.ops.reduce_by_key(keys, vals, 1)
         out_split = even_splitters(new_shape, self.world)

@@ -435,3 +435,32 @@ def test_config4_full_size_properties(sp):
     del D
     Q = W * W
     assert Q.nnz == n and bool((Q.indices == idx).all().item()) and bool((Q.data == val * val).all().item())
+
+
+def test_axis_accumulate_and_emit_ranges(sp):
+    """The two halves of the dense axis sum on caller-owned buffers (what the sharded sum all-reduces
+    in between): accumulating two halves of an operand separately and emitting the cells in two
+    64-aligned ranges gives the oracle's sum(axis)."""
+    import torch
+    from sparray_b200 import _kernels as k, _plan
+    rng = np.random.default_rng(12)
+    shape = (37, 29, 23)
+    idx, val = rand_operand(rng, shape, 6000, np.float32)
+    for axis in (0, 1):
+        _, in_s, out_s, _ = _plan.axis_sum_plan(shape, axis)
+        cells = int(np.prod(shape)) // shape[axis]
+        half = len(idx) // 2
+        ti, tv = torch.from_numpy(idx).cuda(), torch.from_numpy(val).cuda()
+        acc1, t1 = k.axis_accumulate(ti[:half].contiguous(), tv[:half].contiguous(), in_s, out_s, cells)
+        acc2, t2 = k.axis_accumulate(ti[half:].contiguous(), tv[half:].contiguous(), in_s, out_s, cells)
+        acc = acc1 + acc2
+        touched = torch.maximum(t1, t2)
+        cut = (cells // 2) // 64 * 64
+        k1, s1 = k.emit_touched(acc, touched, 0, cut)
+        k2, s2 = k.emit_touched(acc, touched, cut, cells)
+        wi, wv, _ = fo.sum_axis(idx, val, shape, axis)
+        got_i = np.concatenate([to_np(k1), to_np(k2)])
+        got_v = np.concatenate([to_np(s1), to_np(s2)])
+        np.testing.assert_array_equal(got_i, wi)
+        np.testing.assert_allclose(got_v, wv, rtol=1e-5, atol=1e-6 * np.abs(wv).max())
+        assert float(acc.abs().sum().item()) == 0.0 and int(touched.sum().item()) == 0    # emitted cells were zeroed

@@ -64,6 +64,19 @@ class OracleOps:
         order = np.argsort((k // div) & ((1 << bits) - 1), kind="stable") if bits else np.arange(len(k))
         return torch.from_numpy(k[order]), val[torch.from_numpy(order)]
 
+    def axis_accumulate(self, idx, val, in_s, out_s, cells):
+        k, _ = self.rekey_sort(idx, val, in_s, out_s, 1, 0)
+        acc = np.zeros(cells)
+        np.add.at(acc, k.numpy(), val.numpy().astype(np.float64))
+        touched = np.zeros((cells + 63) // 64 * 64, dtype=np.uint8)
+        touched[k.numpy()] = 1
+        return torch.from_numpy(acc), torch.from_numpy(touched)
+
+    def emit_touched(self, acc, touched, lo, hi):
+        assert lo % 64 == 0 or lo == hi
+        sel = np.nonzero(touched.numpy()[lo:hi])[0] + lo
+        return torch.from_numpy(sel.astype(np.int64)), acc[torch.from_numpy(sel)]
+
     def spmv(self, idx, val, ncols, nrows, x):
         i = idx.numpy()
         y = np.bincount(i // ncols, val.numpy().astype(np.float64) * x.numpy()[i % ncols].astype(np.float64), minlength=nrows)
@@ -113,15 +126,19 @@ def _worker(rank, world, port, results):
         n_loc = A2.nnz_local
         assert abs(n_loc - len(ai) / world) < 0.2 * len(ai)
 
-        # axis sums: last axis (border fix-up, splitters inside a row), middle axis, first axis
-        for arr, full in ((A, (ai, av)), (A2, (ai, av)), (B, (bi, bv))):
-            for axis in (2, 1, 0):
-                S = arr.sum(axis)
-                gi, gv = S.gather()
-                wi, wv, wshape = fo.sum_axis(full[0], full[1], shape, axis)
-                assert S.shape == tuple(wshape)
-                assert np.array_equal(gi, wi), (axis, gi[:10], wi[:10])
-                np.testing.assert_allclose(gv, wv, rtol=1e-12, atol=1e-12)
+        # axis sums: last axis (border fix-up, splitters inside a row), middle axis, first axis;
+        # other axes through the dense accumulators + all-reduce, then again through the
+        # exchange of partial sums that large outputs take
+        for dense_limit in (sh.DENSE_ALLREDUCE_MAX_CELLS, 0):
+            sh.DENSE_ALLREDUCE_MAX_CELLS = dense_limit
+            for arr, full in ((A, (ai, av)), (A2, (ai, av)), (B, (bi, bv))):
+                for axis in (2, 1, 0):
+                    S = arr.sum(axis)
+                    gi, gv = S.gather()
+                    wi, wv, wshape = fo.sum_axis(full[0], full[1], shape, axis)
+                    assert S.shape == tuple(wshape)
+                    assert np.array_equal(gi, wi), (axis, gi[:10], wi[:10])
+                    np.testing.assert_allclose(gv, wv, rtol=1e-12, atol=1e-12)
 
         # transpose: re-key, exchange by new-key range, local sort
         for axes in ((2, 1, 0), (1, 0, 2), (0, 2, 1)):
