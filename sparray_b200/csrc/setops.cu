@@ -307,8 +307,9 @@ struct Cfg {
     // no merging warp is held up by the L2 round trips
     static constexpr int kHelperWarp = KIND == KIND_UNION ? kNT / 32 : 0;
     static constexpr int kThreads = KIND == KIND_UNION ? kNT + 32 : kNT;
-    static constexpr int kMinCtas = !kStageVals ? 6 : (sizeof(V) == 8 ? 3 : 4);   // what shared memory allows   // what shared memory allows
-    using L = Layout<kVT, kStageVals ? (int)sizeof(V) : 0, kNBuf, KIND == KIND_INTERSECT ? 0 : kCap * 8, kPayload>;
+    static constexpr int kMinCtas = !kStageVals ? 6 : (sizeof(V) == 8 ? 3 : 5);   // what shared memory allows
+    // unions stage their output keys as 32-bit tile-local offsets (tiles spanning >= 2^32 store directly)
+    using L = Layout<kVT, kStageVals ? (int)sizeof(V) : 0, kNBuf, KIND == KIND_INTERSECT ? 0 : kCap * 4, kPayload>;
 };
 
 struct EdgeReg {         // an unaligned head / tail element riding in a register until its buffer is live
@@ -456,7 +457,7 @@ setop_kernel(const SetopParams p) {
     int64_t* base_s = reinterpret_cast<int64_t*>(smem + 96);
     char* buf = smem + L::kHeader;
     char* stg = buf + L::kBuf;
-    int64_t* skey = reinterpret_cast<int64_t*>(stg);                    // compacted outputs
+    uint32_t* skey = reinterpret_cast<uint32_t*>(stg);                  // compacted outputs (keys minus the tile base)
     VO* sval = reinterpret_cast<VO*>(stg + L::kStgKeys);
     uint8_t* slut = reinterpret_cast<uint8_t*>(stg + L::kStgKeys);
     int64_t* spa = reinterpret_cast<int64_t*>(stg + L::kStgKeys);
@@ -599,7 +600,7 @@ setop_kernel(const SetopParams p) {
 
     // ---- materialise the emitted items: unions into the shared staging area (stored coalesced
     //      below); intersections -- few outputs -- straight to their reserved global slots -----------
-    int64_t* ek = skey;
+    int64_t* ek = nullptr;
     VO* ev = sval;
     int64_t *epa = spa, *epb = spb_;
     if constexpr (KIND == KIND_INTERSECT) {
@@ -636,49 +637,65 @@ setop_kernel(const SetopParams p) {
     } else {
         const V* Av = STAGE_VALS ? reinterpret_cast<const V*>(buf + g.offAv) : nullptr;
         const V* Bv = STAGE_VALS ? reinterpret_cast<const V*>(buf + g.offBv) : nullptr;
-        int ai = ai0, bi = bi0;
+        // one emission loop, two sinks: the shared staging area (32-bit keys; the normal case) or, for a
+        // tile whose keys span >= 2^32, global memory directly once the tile's offset is known
+        auto emit = [&](auto put_key, VO* out_v, uint8_t* out_lut) {
+            int ai = ai0, bi = bi0;
 #pragma unroll
-        for (int k = 0; k < kVT; ++k) {
-            const bool ta = (m_ta >> k) & 1u, eq = ta && ((m_eq >> k) & 1u), e = (m_emit >> k) & 1u;
-            if (e) {
-                ek[off] = ta ? As64[ai] : Bs64[bi];
-                if constexpr (HAS_VAL) {
-                    const V x = ta ? Av[ai] : V(0);
-                    V y = (!ta || eq) ? Bv[bi] : V(0);
-                    if (p.negate_b && (!ta || eq)) y = (V)(-y);
-                    if constexpr (sizeof(VO) == sizeof(V)) {
-                        // assignment semantics: the stored b wins, a survives where b is absent
-                        ev[off] = p.op == SPB_OVERRIDE ? (VO)((!ta || eq) ? y : x) : value_op<V, VO>(p.op, x, y);
-                    } else {
-                        ev[off] = value_op<V, VO>(p.op, x, y);
+            for (int k = 0; k < kVT; ++k) {
+                const bool ta = (m_ta >> k) & 1u, eq = ta && ((m_eq >> k) & 1u), e = (m_emit >> k) & 1u;
+                if (e) {
+                    put_key(off, ta, ai, bi);
+                    if constexpr (HAS_VAL) {
+                        const V x = ta ? Av[ai] : V(0);
+                        V y = (!ta || eq) ? Bv[bi] : V(0);
+                        if (p.negate_b && (!ta || eq)) y = (V)(-y);
+                        if constexpr (sizeof(VO) == sizeof(V)) {
+                            // assignment semantics: the stored b wins, a survives where b is absent
+                            out_v[off] = p.op == SPB_OVERRIDE ? (VO)((!ta || eq) ? y : x) : value_op<V, VO>(p.op, x, y);
+                        } else {
+                            out_v[off] = value_op<V, VO>(p.op, x, y);
+                        }
+                    }
+                    if constexpr (SEAM) {
+                        if (out_lut) out_lut[off] = ta ? (eq ? 2 : 0) : 1;
+                    }
+                    ++off;
+                }
+                if constexpr (SEAM) {
+                    if (k < steps) {
+                        if (ta) {
+                            if (p.a_only) p.a_only[g.a0 + ai] = eq ? 0 : 1;
+                        } else {
+                            if (p.b_only) p.b_only[g.b0 + bi] = e ? 1 : 0;
+                        }
                     }
                 }
-                if constexpr (SEAM) slut[off] = ta ? (eq ? 2 : 0) : 1;
-                ++off;
+                ai += ta ? 1 : 0;
+                bi += ta ? 0 : ((k < steps) ? 1 : 0);
             }
-            if constexpr (SEAM) {
-                if (k < steps) {
-                    if (ta) {
-                        if (p.a_only) p.a_only[g.a0 + ai] = eq ? 0 : 1;
-                    } else {
-                        if (p.b_only) p.b_only[g.b0 + bi] = e ? 1 : 0;
-                    }
+        };
+        VO* const o_val = reinterpret_cast<VO*>(p.out_val);
+        if (narrow) {
+            const NarrowKeys A{reinterpret_cast<const uint32_t*>(As64), (uint32_t)kbase};
+            const NarrowKeys B{reinterpret_cast<const uint32_t*>(Bs64), (uint32_t)kbase};
+            emit([&](int o, bool ta, int ai, int bi) { skey[o] = ta ? A(ai) : B(bi); }, sval, slut);
+            sync_mergers<KIND>();                                      // (D) staging complete
+            mbar_wait(ready_bar, 0);                                   // offset resolved by the helper warp
+            const int64_t base = *base_s;
+            for (int i = tid; i < tile_total; i += kNT) {
+                p.out_idx[base + i] = kbase + (int64_t)skey[i];
+                if constexpr (HAS_VAL) o_val[base + i] = sval[i];
+                if constexpr (SEAM) {
+                    if (p.lut) p.lut[base + i] = slut[i];
                 }
             }
-            ai += ta ? 1 : 0;
-            bi += ta ? 0 : ((k < steps) ? 1 : 0);
-        }
-    }
-    if constexpr (KIND == KIND_INTERSECT) return;
-    sync_mergers<KIND>();                                              // (D) staging complete
-    mbar_wait(ready_bar, 0);                                           // offset resolved by the helper warp
-    const int64_t base = *base_s;
-    VO* const o_val = reinterpret_cast<VO*>(p.out_val);
-    for (int i = tid < kNT ? tid : tile_total; i < tile_total; i += kNT) {
-        p.out_idx[base + i] = skey[i];
-        if constexpr (HAS_VAL) o_val[base + i] = sval[i];
-        if constexpr (SEAM && KIND == KIND_UNION) {
-            if (p.lut) p.lut[base + i] = slut[i];
+        } else {
+            mbar_wait(ready_bar, 0);
+            const int64_t base = *base_s;
+            int64_t* const ok = p.out_idx + base;
+            emit([&](int o, bool ta, int ai, int bi) { ok[o] = ta ? As64[ai] : Bs64[bi]; }, o_val + base,
+                 p.lut ? p.lut + base : nullptr);
         }
     }
 }

@@ -206,3 +206,29 @@ def test_host_buffer_seam(sp):
     w = fo.intersect1d_sorted(a, b, return_inds=True)
     for g, ww in zip((out, ia, ib), w):
         np.testing.assert_array_equal(g[:cnt.value], ww)
+
+
+def test_wide_key_tiles(sp):
+    """Every tile spans far more than 2^32 (keys are multiples of 2^33): the 64-bit key path of the
+    merge, including the unions' direct-to-global emission, against the oracle."""
+    rng = np.random.default_rng(33)
+    n = 30000
+    a = (np.unique(rng.integers(0, 2 ** 29, n)) << 33).astype(np.int64)
+    b = (np.unique(rng.integers(0, 2 ** 29, n)) << 33).astype(np.int64)
+    b[::7] = a[:len(b[::7])] if len(a) >= len(b[::7]) else b[::7]        # force some matches
+    b = np.unique(b)
+    av = rng.standard_normal(len(a)).astype(np.float32)
+    bv = rng.standard_normal(len(b)).astype(np.float32)
+    shape = (2 ** 62,)
+    A = sp.FlatSparray(a, av, shape=shape, is_canonical=True)
+    B = sp.FlatSparray(b, bv, shape=shape, is_canonical=True)
+    for op, uf in (("add", np.add), ("maximum", np.maximum)):
+        wi, wv = fo.pairwise_union(a, av, b, bv, uf)
+        got = A + B if op == "add" else A.maximum(B)
+        assert_sparse_same(got, (wi, wv, shape))
+    wi, wv = fo.pairwise_intersect(a, av, b, bv, np.multiply)
+    assert len(wi) > 100
+    assert_sparse_same(A * B, (wi, wv, shape))
+    from sparray_b200 import compat as sc
+    for got, want in zip(sc.union1d_sorted(a, b, return_masks=True), fo.union1d_sorted(a, b, return_masks=True)):
+        np.testing.assert_array_equal(to_np(got).astype(want.dtype), want)
