@@ -11,16 +11,17 @@ sys.path.insert(0, os.path.join(os.path.dirname(__file__)))
 from run_kernels import synth
 
 def main():
+  for tdt, sdt, tag in ((torch.float32, dt.SPB_F32, "f32"), (torch.float64, dt.SPB_F64, "f64")):
     size = 256 * 256 * 256 * 64
-    ai, av = synth(10_700_000, size, torch.float32, 1)
-    bi, bv = synth(10_700_000, size, torch.float32, 2)
+    ai, av = synth(10_700_000, size, tdt, 1)
+    bi, bv = synth(10_700_000, size, tdt, 2)
     na, nb = ai.numel(), bi.numel()
     out_idx = torch.empty(na + nb, dtype=torch.int64, device="cuda")
-    out_val = torch.empty(na + nb, dtype=torch.float32, device="cuda")
+    out_val = torch.empty(na + nb, dtype=tdt, device="cuda")
     cnt = torch.empty(1, dtype=torch.int64, device="cuda")
-    for name, fn, op in (("intersect", lib.spb_intersect_binop, "mul"), ("union", lib.spb_union_binop, "add")):
+    for name, fn, op in (("intersect " + tag, lib.spb_intersect_binop, "mul"), ("union " + tag, lib.spb_union_binop, "add")):
         def launch():
-            check(fn(dt.BINOPS[op], dt.SPB_F32, ptr(ai), ptr(av), na, ptr(bi), ptr(bv), nb, ptr(out_idx), ptr(out_val),
+            check(fn(dt.BINOPS[op], sdt, ptr(ai), ptr(av), na, ptr(bi), ptr(bv), nb, ptr(out_idx), ptr(out_val),
                      ptr(cnt), workspace(), stream()))
         for _ in range(5):
             launch()

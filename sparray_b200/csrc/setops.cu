@@ -15,7 +15,7 @@
 //   2. setop_kernel: ONE tile per CTA, in blockIdx order; 6 (intersections) or 3-4 (unions) CTAs per
 //      SM hide each other's latencies.  Per tile
 //        - the staging warp loads the descriptor and issues TMA bulk copies (cp.async.bulk +
-//          mbarrier) of the A / B index ranges (unions: and the value ranges); the < 16-byte
+//          mbarrier) of the A / B index ranges (values are never staged); the < 16-byte
 //          unaligned heads / tails and the halo keys ride in registers of that warp;
 //        - the staged 64-bit keys are read as 32-bit tile-local offsets whenever the tile's key
 //          span allows it (64-bit path otherwise), so the merge runs on single-register keys;
@@ -26,7 +26,7 @@
 //        - block scan of the output counts; then
 //          unions: a helper warp has been resolving the tile's output offset by decoupled
 //          look-back since the tile was staged; items are materialised into a shared staging area
-//          (value op applied) and stored coalesced;
+//          (32-bit keys; values read from global exactly once, op applied) and stored coalesced;
 //          intersections: no look-back -- the tile owns private output slots (one atomic only if
 //          it overflows them), only the set bits of the match mask are visited, the two values of
 //          a match are gathered straight from global memory (unmatched values are never read).
@@ -129,22 +129,18 @@ constexpr int key_region_bytes(int vt) { return (kNT * vt + 4) * 8 + 128 + vt * 
 // Half-warps search the tile diagonals (16-ary, bracketed around the proportional guess); one thread
 // per tile then works out everything the merge kernel needs to stage the tile -- so that kernel's
 // staging warp only loads 128 bytes and issues the copies.
-//   word 0..4 : the Geom record (a0, b0, an|bn, offA|offB, offAv|offBv)
-//   word 5..8 : 16-byte aligned global source of the TMA copy of A keys, B keys, A values, B values
-//   word 9    : 4 x 16 bit  destination offsets inside the tile buffer
-//   word 10   : 4 x 16 bit  TMA byte counts
-//   word 11   : 4 x (4 bit head count, 4 bit tail count): elements before / after the aligned middle
+//   word 0..3 : the Geom record (a0, b0, an|bn, offA|offB)
+//   word 5..6 : 16-byte aligned global source of the TMA copy of the A keys, the B keys
+//   word 9    : 2 x 16 bit  destination offsets inside the tile buffer
+//   word 10   : 2 x 16 bit  TMA byte counts
+//   word 11   : 2 x (4 bit head count, 4 bit tail count): elements before / after the aligned middle
 constexpr int kDescWords = 16;
 
 struct PartitionParams {
     const int64_t* a;
     const int64_t* b;
     int64_t na, nb;
-    const void* a_val;
-    const void* b_val;
-    int val_esize;           // 0: values are not staged
     int tile_items;          // merged items per tile
-    int key_reg;             // bytes of the key region of a tile buffer
     int64_t ntiles;
     uint64_t* desc;          // [ntiles][kDescWords]
 };
@@ -212,30 +208,21 @@ __global__ void __launch_bounds__(256) merge_partition_kernel(const PartitionPar
     __syncthreads();
     const int64_t t = (int64_t)blockIdx.x * kPartTiles + threadIdx.x;
     if (threadIdx.x >= kPartTiles || t >= p.ntiles) return;
-    const int kKeyReg = p.key_reg;
     const int64_t total = p.na + p.nb;
     const int64_t d0 = t * (int64_t)p.tile_items;
     const int64_t d1 = (d0 + p.tile_items < total) ? d0 + p.tile_items : total;
     const int64_t a0 = s_split[threadIdx.x], a1 = s_split[threadIdx.x + 1];
     const int64_t b0 = d0 - a0, b1 = d1 - a1;
-    // indices [x0-1, x1] (one halo key either side), values [x0, x1) (+1 for B: partner of the last A)
+    // indices [x0-1, x1] (one halo key either side); values are never staged: the merge kernel reads
+    // the few it needs (intersections) or each exactly once (unions) straight from global memory
     const int64_t ga_lo = a0 > 0 ? a0 - 1 : 0, ga_hi = a1 < p.na ? a1 + 1 : p.na;
     const int64_t gb_lo = b0 > 0 ? b0 - 1 : 0, gb_hi = b1 < p.nb ? b1 + 1 : p.nb;
-    StagePlan pl[4];
-    int dst0[4];             // buffer offset that the plan's g_al maps to
+    StagePlan pl[2];
+    int dst0[2];             // buffer offset that the plan's g_al maps to
     pl[0] = make_stage_plan(p.a, ga_lo, ga_hi, 8);
     pl[1] = make_stage_plan(p.b, gb_lo, gb_hi, 8);
     dst0[0] = 16;                                                     // front pad: slot for index -1
     dst0[1] = dst0[0] + (int)((pl[0].span_bytes() + 15) & ~15u) + 32; // A's +1 sentinel, B's -1 slot
-    const int E = p.val_esize;
-    int narr = 2;
-    if (E) {
-        narr = 4;
-        pl[2] = make_stage_plan(p.a_val, a0, a1, E);
-        pl[3] = make_stage_plan(p.b_val, b0, gb_hi > b1 ? b1 + 1 : b1, E);
-        dst0[2] = kKeyReg;
-        dst0[3] = dst0[2] + (int)((pl[2].span_bytes() + 15) & ~15u) + 16;
-    }
     uint64_t* d = p.desc + t * kDescWords;
     d[0] = (uint64_t)a0;
     d[1] = (uint64_t)b0;
@@ -243,29 +230,18 @@ __global__ void __launch_bounds__(256) merge_partition_kernel(const PartitionPar
     const int offA = dst0[0] + (int)(pl[0].p_lo - pl[0].g_al) + (int)(a0 - ga_lo) * 8;
     const int offB = dst0[1] + (int)(pl[1].p_lo - pl[1].g_al) + (int)(b0 - gb_lo) * 8;
     d[3] = (uint64_t)(uint32_t)offA | ((uint64_t)(uint32_t)offB << 32);
-    int offAv = 0, offBv = 0;
-    if (E) {
-        offAv = dst0[2] + (int)(pl[2].p_lo - pl[2].g_al);
-        offBv = dst0[3] + (int)(pl[3].p_lo - pl[3].g_al);
-    }
-    d[4] = (uint64_t)(uint32_t)offAv | ((uint64_t)(uint32_t)offBv << 32);
     uint64_t w_dst = 0, w_cnt = 0, w_ht = 0;
-    for (int i = 0; i < 4; ++i) {
-        uint64_t src = 0;
-        if (i < narr) {
-            const StagePlan& s = pl[i];
-            const int es = i < 2 ? 8 : E;
-            const uintptr_t head_end = s.q_lo < s.p_hi ? s.q_lo : s.p_hi;      // == q_lo unless the range is tiny
-            const uintptr_t mid = head_end;                                    // the copy starts here
-            const uint32_t bytes = s.tma_bytes();
-            const uintptr_t tail_lo = mid + bytes;
-            src = (uint64_t)mid;
-            w_dst |= (uint64_t)(uint32_t)(dst0[i] + (int)(mid - s.g_al)) << (16 * i);
-            w_cnt |= (uint64_t)bytes << (16 * i);
-            const uint32_t nh = (uint32_t)((mid - s.p_lo) / es), nt = (uint32_t)((s.p_hi - tail_lo) / es);
-            w_ht |= (uint64_t)(nh | (nt << 4)) << (8 * i);
-        }
-        d[5 + i] = src;
+    for (int i = 0; i < 2; ++i) {
+        const StagePlan& s = pl[i];
+        const uintptr_t head_end = s.q_lo < s.p_hi ? s.q_lo : s.p_hi;      // == q_lo unless the range is tiny
+        const uintptr_t mid = head_end;                                    // the copy starts here
+        const uint32_t bytes = s.tma_bytes();
+        const uintptr_t tail_lo = mid + bytes;
+        w_dst |= (uint64_t)(uint32_t)(dst0[i] + (int)(mid - s.g_al)) << (16 * i);
+        w_cnt |= (uint64_t)bytes << (16 * i);
+        const uint32_t nh = (uint32_t)((mid - s.p_lo) / 8), nt = (uint32_t)((s.p_hi - tail_lo) / 8);
+        w_ht |= (uint64_t)(nh | (nt << 4)) << (8 * i);
+        d[5 + i] = (uint64_t)mid;
     }
     d[9] = w_dst;
     d[10] = w_cnt;
@@ -277,97 +253,73 @@ struct Geom {            // where a staged tile lives inside its buffer
     int64_t a0, b0;
     int an, bn;
     int offA, offB;      // byte offset of As64[0] / Bs64[0] from the buffer start
-    int offAv, offBv;    // byte offset of Av[0] / Bv[0]
 };
 
-template <int VT, int VBYTES, int NBUF, int OUT_KEYS, int OUT_PAYLOAD>   // items/thread; staged value bytes; buffers; staging bytes
+template <int VT, int OUT_KEYS, int OUT_PAYLOAD>   // items/thread; staging bytes (keys, values / lut)
 struct Layout {
     static constexpr int kTile = kNT * VT;
     static constexpr int kHeader = 256;
-    static constexpr int kKeyReg = key_region_bytes(VT);
-    static constexpr int kValReg = VBYTES ? kTile * VBYTES + 96 : 0;
-    static constexpr int kBuf = kKeyReg + kValReg;                       // one staged input tile
+    static constexpr int kBuf = key_region_bytes(VT);                    // the staged input keys of one tile
     static constexpr int kStgKeys = OUT_KEYS;                            // compacted outputs waiting for their offset
     static constexpr int kStg = ((OUT_KEYS + OUT_PAYLOAD) + 15) & ~15;
-    static constexpr int kTotal = kHeader + NBUF * kBuf + kStg;
-    static_assert(kKeyReg % 16 == 0 && kValReg % 16 == 0, "buffers must stay 16-byte aligned for TMA");
+    static constexpr int kTotal = kHeader + kBuf + kStg;
+    static_assert(kBuf % 16 == 0, "the buffer must stay 16-byte aligned for TMA");
 };
 
 template <typename V, typename VO, int KIND, bool HAS_VAL, bool SEAM>
 struct Cfg {
-    static constexpr bool kStageVals = HAS_VAL && KIND == KIND_UNION;
     static constexpr int kVT = KIND == KIND_UNION ? 8 : 16;
     static constexpr int kTile = kNT * kVT;
     static constexpr int kFixedSlots = 8 * kVT;                          // private output slots per tile (intersections)
     static constexpr int kCap = KIND == KIND_UNION ? kTile : kTile / 2;  // outputs per tile, at most
     static constexpr int kPayload = KIND == KIND_INTERSECT ? 0
                                     : (HAS_VAL ? kCap * (int)sizeof(VO) : (SEAM ? kCap : 0));
-    static constexpr int kNBuf = 1;
     // unions resolve their output offset by look-back: a ninth warp does it (and the staging) so that
     // no merging warp is held up by the L2 round trips
     static constexpr int kHelperWarp = KIND == KIND_UNION ? kNT / 32 : 0;
     static constexpr int kThreads = KIND == KIND_UNION ? kNT + 32 : kNT;
-    static constexpr int kMinCtas = !kStageVals ? 6 : (sizeof(V) == 8 ? 3 : 5);   // what shared memory allows
-    // unions stage their output keys as 32-bit tile-local offsets (tiles spanning >= 2^32 store directly)
-    using L = Layout<kVT, kStageVals ? (int)sizeof(V) : 0, kNBuf, KIND == KIND_INTERSECT ? 0 : kCap * 4, kPayload>;
+    static constexpr int kMinCtas = (KIND == KIND_UNION && HAS_VAL && sizeof(VO) == 8) ? 5 : 6;   // what shared memory allows
+    // unions stage their output keys as 32-bit tile-local offsets (tiles spanning >= 2^32 store directly);
+    // input values are never staged: every one is read exactly once, straight from global memory
+    using L = Layout<kVT, KIND == KIND_INTERSECT ? 0 : kCap * 4, kPayload>;
 };
 
-struct EdgeReg {         // an unaligned head / tail element riding in a register until its buffer is live
+struct EdgeReg {         // an unaligned head / tail key riding in a register until its buffer is live
     uint64_t raw;
     uint32_t dst;        // shared-memory address, 0 = nothing
-    uint32_t size;
 };
 
 __device__ __forceinline__ void edge_store(const EdgeReg& er) {
-    if (er.dst) {
-        if (er.size == 8) asm volatile("st.shared.u64 [%0], %1;" ::"r"(er.dst), "l"(er.raw) : "memory");
-        else asm volatile("st.shared.u32 [%0], %1;" ::"r"(er.dst), "r"((uint32_t)er.raw) : "memory");
-    }
+    if (er.dst) asm volatile("st.shared.u64 [%0], %1;" ::"r"(er.dst), "l"(er.raw) : "memory");
 }
 
-// Executed by the whole of warp 0: put one tile in flight.  `dw` is this lane's word of the
-// tile descriptor (lanes 0..15).  Lanes 0..3 each issue one TMA bulk copy, lanes 16..31 each
-// pick up one ragged-edge element in a register, lanes 0..4 publish the geometry.
-template <int VBYTES>
+// Executed by the whole staging warp: put one tile in flight.  `dw` is this lane's word of the
+// tile descriptor (lanes 0..15).  Lanes 0..1 each issue one TMA bulk copy (A keys, B keys), lanes
+// 16..19 each pick up one ragged-edge key (an 8-byte element in front of / behind the 16-byte
+// aligned middle) in a register, lanes 0..3 publish the geometry.
 __device__ __forceinline__ void prefetch_tile(uint64_t dw, char* buf, uint64_t* bar, Geom* g, EdgeReg& er, int lane) {
-    if (lane < 5) reinterpret_cast<uint64_t*>(g)[lane] = dw;
+    if (lane < 4) reinterpret_cast<uint64_t*>(g)[lane] = dw;
     const uint64_t w_dst = __shfl_sync(0xffffffffu, dw, 9);
     const uint64_t w_cnt = __shfl_sync(0xffffffffu, dw, 10);
     const uint32_t w_ht = (uint32_t)__shfl_sync(0xffffffffu, dw, 11);
-    // which array this lane serves: TMA lanes by index, edge lanes by slot
-    const int s = lane - 16;                                          // edge slot 0..15
-    int arr = lane & 3;
-    int tail = 0, j = 0;
-    if (lane >= 16) {
-        arr = s < 2 ? 0 : (s < 4 ? 1 : (s < 10 ? 2 : 3));
-        const int r = s < 4 ? 0 : (s - 4) % 6;
-        tail = s < 4 ? (s & 1) : (r >= 3);
-        j = s < 4 ? 0 : r % 3;
-    }
+    // which array this lane serves: TMA lanes by index, edge lanes by slot (A head, A tail, B head, B tail)
+    const int s = lane - 16;
+    const int arr = lane >= 16 ? ((s >> 1) & 1) : (lane & 1);
+    const int tail = s & 1;
     const uint64_t src = __shfl_sync(0xffffffffu, dw, 5 + arr);
     const uint32_t dst = (uint32_t)(w_dst >> (16 * arr)) & 0xffffu;
     const uint32_t bytes = (uint32_t)(w_cnt >> (16 * arr)) & 0xffffu;
-    if (lane == 0) {
-        const uint32_t total = (uint32_t)(w_cnt & 0xffffu) + (uint32_t)((w_cnt >> 16) & 0xffffu) +
-                               (uint32_t)((w_cnt >> 32) & 0xffffu) + (uint32_t)((w_cnt >> 48) & 0xffffu);
-        mbar_arrive_expect_tx(bar, total);
-    }
+    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(w_cnt & 0xffffu) + (uint32_t)((w_cnt >> 16) & 0xffffu));
     __syncwarp();
-    if (lane < 4 && bytes) tma_bulk_g2s(buf + dst, reinterpret_cast<const void*>(src), bytes, bar);
+    if (lane < 2 && bytes) tma_bulk_g2s(buf + dst, reinterpret_cast<const void*>(src), bytes, bar);
     er.dst = 0;
-    er.size = 0;
     er.raw = 0;
-    if (lane >= 16 && src) {
-        const int E = arr < 2 ? 8 : VBYTES;
+    if (lane >= 16 && lane < 20 && src) {
         const int nh = (int)(w_ht >> (8 * arr)) & 15, nt = (int)(w_ht >> (8 * arr + 4)) & 15;
-        const int n = tail ? nt : nh;
-        if (E && j < n) {
-            const int64_t delta = tail ? (int64_t)bytes + (int64_t)j * E : -(int64_t)(nh - j) * E;
-            const uintptr_t addr = (uintptr_t)((int64_t)src + delta);
+        if ((tail ? nt : nh) > 0) {
+            const int64_t delta = tail ? (int64_t)bytes : -8;
             er.dst = smem_u32(buf + dst) + (uint32_t)(int32_t)delta;
-            er.size = (uint32_t)E;
-            if (E == 8) er.raw = __ldg(reinterpret_cast<const unsigned long long*>(addr));
-            else er.raw = __ldg(reinterpret_cast<const unsigned int*>(addr));
+            er.raw = __ldg(reinterpret_cast<const unsigned long long*>((uintptr_t)((int64_t)src + delta)));
         }
     }
 }
@@ -445,8 +397,6 @@ __global__ void __launch_bounds__(Cfg<V, VO, KIND, HAS_VAL, SEAM>::kThreads, Cfg
 setop_kernel(const SetopParams p) {
     using C = Cfg<V, VO, KIND, HAS_VAL, SEAM>;
     using L = typename C::L;
-    constexpr bool STAGE_VALS = C::kStageVals;
-    constexpr int VB = STAGE_VALS ? (int)sizeof(V) : 0;
     constexpr int kVT = C::kVT;
     constexpr int kFixedSlots = C::kFixedSlots;
     constexpr int kHelper = C::kHelperWarp;
@@ -485,7 +435,7 @@ setop_kernel(const SetopParams p) {
         // ---- stage the tile: descriptor -> TMA bulk copies, ragged edges, sentinels -------------
         const uint64_t dw = lane < kDescWords ? __ldg(p.desc + tile * kDescWords + lane) : 0;
         EdgeReg er;
-        prefetch_tile<VB>(dw, buf, full, geom, er, lane);
+        prefetch_tile(dw, buf, full, geom, er, lane);
         edge_store(er);
         const int64_t a0 = (int64_t)__shfl_sync(0xffffffffu, dw, 0), b0 = (int64_t)__shfl_sync(0xffffffffu, dw, 1);
         const uint64_t nn = __shfl_sync(0xffffffffu, dw, 2), oo = __shfl_sync(0xffffffffu, dw, 3);
@@ -635,20 +585,23 @@ setop_kernel(const SetopParams p) {
         }
         return;
     } else {
-        const V* Av = STAGE_VALS ? reinterpret_cast<const V*>(buf + g.offAv) : nullptr;
-        const V* Bv = STAGE_VALS ? reinterpret_cast<const V*>(buf + g.offBv) : nullptr;
+        // every input value is used exactly once: read it where it is needed, straight from global
+        // memory (a thread's items are contiguous runs of A and of B, neighbours share the cache lines)
+        const V* const Av = reinterpret_cast<const V*>(p.a_val) + g.a0;
+        const V* const Bv = reinterpret_cast<const V*>(p.b_val) + g.b0;
         // one emission loop, two sinks: the shared staging area (32-bit keys; the normal case) or, for a
         // tile whose keys span >= 2^32, global memory directly once the tile's offset is known
         auto emit = [&](auto put_key, VO* out_v, uint8_t* out_lut) {
             int ai = ai0, bi = bi0;
 #pragma unroll
             for (int k = 0; k < kVT; ++k) {
-                const bool ta = (m_ta >> k) & 1u, eq = ta && ((m_eq >> k) & 1u), e = (m_emit >> k) & 1u;
+                const bool ta = (m_ta >> k) & 1u, e = (m_emit >> k) & 1u;
+                [[maybe_unused]] const bool eq = ta && ((m_eq >> k) & 1u);
                 if (e) {
                     put_key(off, ta, ai, bi);
                     if constexpr (HAS_VAL) {
-                        const V x = ta ? Av[ai] : V(0);
-                        V y = (!ta || eq) ? Bv[bi] : V(0);
+                        const V x = ta ? __ldg(Av + ai) : V(0);
+                        V y = (!ta || eq) ? __ldg(Bv + bi) : V(0);
                         if (p.negate_b && (!ta || eq)) y = (V)(-y);
                         if constexpr (sizeof(VO) == sizeof(V)) {
                             // assignment semantics: the stored b wins, a survives where b is absent
@@ -784,11 +737,9 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
         if (ctas_per_sm < 1) return SPB_ERR_UNSUPPORTED;
     }
     PartitionParams pp{};
-    pp.a = p.a; pp.b = p.b; pp.na = p.na; pp.nb = p.nb; pp.a_val = p.a_val; pp.b_val = p.b_val;
-    pp.val_esize = Cfg<V, VO, KIND, HAS_VAL, SEAM>::kStageVals ? (int)sizeof(V) : 0;
+    pp.a = p.a; pp.b = p.b; pp.na = p.na; pp.nb = p.nb;
     pp.ntiles = ntiles;
     pp.tile_items = kTile;
-    pp.key_reg = C::L::kKeyReg;
     pp.desc = reinterpret_cast<uint64_t*>(ws->payload);
     char* pay = reinterpret_cast<char*>(ws->payload);
     if (KIND == KIND_INTERSECT) {
