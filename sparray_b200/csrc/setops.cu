@@ -12,7 +12,7 @@
 //   1. merge_partition_kernel: a half-warp per tile boundary finds the merge-path split of its
 //      diagonal on the two global arrays (bracketed around the proportional guess, then 16-ary);
 //      one thread per tile turns two neighbouring splits into a 128-byte staging descriptor.
-//   2. setop_kernel: ONE tile per CTA, in blockIdx order; 6 (intersections) or 3-4 (unions) CTAs per
+//   2. setop_kernel: ONE tile per CTA, in blockIdx order; 8 (intersections) or 5-6 (unions) CTAs per
 //      SM hide each other's latencies.  Per tile
 //        - the staging warp loads the descriptor and issues TMA bulk copies (cp.async.bulk +
 //          mbarrier) of the A / B index ranges (values are never staged); the < 16-byte
@@ -120,9 +120,9 @@ struct SetopParams {
 enum { KIND_UNION = 0, KIND_INTERSECT = 1 };
 
 constexpr int kNT = 256;   // threads per CTA
-// merged items per thread: 16 for intersections (no value staging, outputs are rare, so the tile can
-// be 4096 items and the per-thread merge-path search is amortised over twice as many items), 8 for
-// unions (values and a full tile of outputs are staged in shared memory)
+// merged items per thread: 12 for intersections (outputs are rare and go straight to global memory, so
+// a 3072-item tile of keys is all the shared memory a CTA needs: 8 CTAs per SM, and the per-thread
+// merge-path search is amortised over more items), 8 for unions (a full tile of outputs is staged)
 constexpr int key_region_bytes(int vt) { return (kNT * vt + 4) * 8 + 128 + vt * 8; }
 
 // ---- launch 1: merge-path split of every tile + its staging descriptor ------------------------
@@ -268,7 +268,7 @@ struct Layout {
 
 template <typename V, typename VO, int KIND, bool HAS_VAL, bool SEAM>
 struct Cfg {
-    static constexpr int kVT = KIND == KIND_UNION ? 8 : 16;
+    static constexpr int kVT = KIND == KIND_UNION ? 8 : 12;
     static constexpr int kTile = kNT * kVT;
     static constexpr int kFixedSlots = 8 * kVT;                          // private output slots per tile (intersections)
     static constexpr int kCap = KIND == KIND_UNION ? kTile : kTile / 2;  // outputs per tile, at most
@@ -278,7 +278,7 @@ struct Cfg {
     // no merging warp is held up by the L2 round trips
     static constexpr int kHelperWarp = KIND == KIND_UNION ? kNT / 32 : 0;
     static constexpr int kThreads = KIND == KIND_UNION ? kNT + 32 : kNT;
-    static constexpr int kMinCtas = (KIND == KIND_UNION && HAS_VAL && sizeof(VO) == 8) ? 5 : 6;   // what shared memory allows
+    static constexpr int kMinCtas = KIND == KIND_INTERSECT ? 8 : ((HAS_VAL && sizeof(VO) == 8) ? 5 : 6);   // what shared memory allows
     // unions stage their output keys as 32-bit tile-local offsets (tiles spanning >= 2^32 store directly);
     // input values are never staged: every one is read exactly once, straight from global memory
     using L = Layout<kVT, KIND == KIND_INTERSECT ? 0 : kCap * 4, kPayload>;
@@ -390,7 +390,7 @@ __device__ __forceinline__ void sync_mergers() {
 }
 
 // One CTA = one tile (blockIdx order, so the decoupled look-back only ever waits on tiles that
-// started earlier).  Latency is hidden across the CTAs resident per SM (6 for intersections, 3-4 for
+// started earlier).  Latency is hidden across the CTAs resident per SM (8 for intersections, 5-6 for
 // unions): while one waits for its TMA copies, others merge or store.
 template <typename V, typename VO, int KIND, bool HAS_VAL, bool SEAM>
 __global__ void __launch_bounds__(Cfg<V, VO, KIND, HAS_VAL, SEAM>::kThreads, Cfg<V, VO, KIND, HAS_VAL, SEAM>::kMinCtas)
