@@ -25,3 +25,7 @@ print("transpose 3210 f32 10.7M: %.0f us" % t(lambda: A.transpose(3, 2, 1, 0)))
 wi, wv = synth(100_000_000, 10 ** 12, torch.float64, 4)
 W = sp.FlatSparray(wi, wv, shape=(10 ** 6, 10 ** 6), is_canonical=True)
 print("sum_axis1 f64 100M: %.0f us" % t(lambda: W.sum(axis=1), reps=5))
+x = torch.randn(10 ** 6, device="cuda", dtype=torch.float64)
+print("spmv f64 100M: %.0f us" % t(lambda: k.spmv(W.indices, W.data, 10 ** 6, 10 ** 6, x, torch.float64), reps=5))
+xs = torch.randn(64, device="cuda", dtype=torch.float32)
+print("spmv f32 10.7M, 64 columns (0.64 elements per row): %.0f us" % t(lambda: k.spmv(ai, av, 64, 256 ** 3, xs, torch.float32)))

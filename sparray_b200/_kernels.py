@@ -289,8 +289,6 @@ DENSE_SUM_ANY_N_CELLS = 1 << 22    # below this the dense path is taken whatever
 def dense_sum_cells(shape, axis):
     """Cell count of sum(axis)'s result if the dense-accumulator path applies whatever nnz is, else 0."""
     from . import _plan
-    if axis == len(shape) - 1:
-        return 0
     cells = _plan.prod(shape) // max(int(shape[axis]), 1)
     return cells if 0 < cells <= DENSE_SUM_ANY_N_CELLS else 0
 
@@ -303,12 +301,14 @@ def sum_axis(idx, val, shape, axis, n_dev=None):
     device count of a producer that was not read back either (only valid when dense_sum_cells())."""
     from . import _plan
     plan = _plan.axis_sum_plan(shape, axis)
+    n = idx.numel()
+    cells = _plan.prod(shape) // max(int(shape[axis]), 1)
     if plan[0] == "last":
-        assert n_dev is None
+        if n_dev is not None or (n and cells <= DENSE_SUM_MAX_CELLS and cells <= 4 * n + DENSE_SUM_ANY_N_CELLS):
+            # the elements of an output cell are contiguous: warp-aggregated atomics into the dense accumulator
+            return axis_sum_dense(idx, val, [plan[1], 1], [1, 0], cells, n_dev)
         return reduce_by_key(idx, val, plan[1]) + (None,)
     _, in_s, out_s, bits = plan
-    n = idx.numel()
-    cells = _plan.prod(shape) // int(shape[axis])
     if n and cells <= DENSE_SUM_MAX_CELLS and cells <= 64 * n + DENSE_SUM_ANY_N_CELLS:
         return axis_sum_dense(idx, val, in_s, out_s, cells, n_dev)
     assert n_dev is None

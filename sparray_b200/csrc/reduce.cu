@@ -439,6 +439,81 @@ int spb_reduce_by_key(int dtype, const int64_t* keys, const void* vals, int64_t 
 #undef SPB_RBK
 }
 
+}  // extern "C" (reopened below)
+
+namespace spb {
+
+// ---- SpMV: y[row] += val * x[col], one atomic per run of equal rows inside a warp ---------------
+// The stored elements are sorted by flat index, so the elements of a row are contiguous: a warp
+// reads 32 consecutive (index, value) pairs coalesced, multiplies by the gathered x, combines runs of
+// equal rows with a segmented shuffle scan and lets the last lane of each run add the run's sum into
+// y (zeroed by the launch wrapper) with ONE float64 atomic.  No shared memory, no barriers, no
+// look-back: ~25 instructions per element row instead of the ~130 of the general segmented reduce.
+constexpr int kSpmvUnroll = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256) spmv_rows_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
+                                                        int64_t n, const FastDiv div, const T* __restrict__ x,
+                                                        double* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t chunk = 32 * kSpmvUnroll;
+    for (int64_t base = warp_global * chunk; base < n; base += nwarps * chunk) {
+        int64_t key[kSpmvUnroll];
+        T v[kSpmvUnroll];
+#pragma unroll
+        for (int u = 0; u < kSpmvUnroll; ++u) {
+            const int64_t i = base + u * 32 + lane;
+            key[u] = i < n ? __ldcs(idx + i) : -1;
+            v[u] = i < n ? __ldcs(val + i) : T(0);
+        }
+        int64_t row[kSpmvUnroll];
+        double prod[kSpmvUnroll];
+#pragma unroll
+        for (int u = 0; u < kSpmvUnroll; ++u) {
+            row[u] = -1;
+            prod[u] = 0.0;
+            if (key[u] >= 0) {
+                row[u] = (int64_t)fastdiv((uint64_t)key[u], div);
+                const int64_t col = key[u] - row[u] * (int64_t)div.d;
+                prod[u] = (double)v[u] * (double)__ldg(x + col);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kSpmvUnroll; ++u) {
+            // segmented inclusive scan over lanes: add the neighbour o lanes below while it is in my row
+            const int64_t rprev = __shfl_up_sync(0xffffffffu, row[u], 1);
+            const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || rprev != row[u]);
+            const int start = 31 - __clz(heads & ((2u << lane) - 1u));       // first lane of my run
+            double s = prod[u];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane - o >= start) s += up;
+            }
+            const bool last = lane == 31 || ((heads >> (lane + 1)) & 1u);
+            if (row[u] >= 0 && last) atomicAdd(y + row[u], s);
+        }
+    }
+}
+
+template <typename T>
+int launch_spmv_rows(const int64_t* idx, const void* vals, int64_t n, int64_t ncols, const void* x, double* y,
+                     cudaStream_t stream) {
+    int64_t blocks = ceil_div(n, 256 * kSpmvUnroll);
+    const int64_t cap = (int64_t)device_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    spmv_rows_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(idx, (const T*)vals, n, make_fastdiv((uint64_t)ncols),
+                                                             (const T*)x, y);
+    SPB_LAUNCHED(1);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace spb
+
+extern "C" {
+
 int spb_spmv(int dtype, const int64_t* idx, const void* vals, int64_t n, int64_t ncols, int64_t nrows,
              const void* x, double* y, spb_workspace* ws, spb_stream_t stream) {
     if (n < 0 || ncols < 1 || nrows < 0) return SPB_ERR_BAD_ARG;
@@ -447,12 +522,10 @@ int spb_spmv(int dtype, const int64_t* idx, const void* vals, int64_t n, int64_t
     SPB_CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)nrows * sizeof(double), stream));
     if (n == 0) return SPB_OK;
     if (!idx || !vals || !x) return SPB_ERR_BAD_ARG;
-    ReduceParams p{};
-    p.keys = idx; p.vals = vals; p.n = n; p.div = make_fastdiv((uint64_t)ncols);
-    p.x = x; p.out_sums = y;
+    (void)ws;
     switch (dtype) {
-        case SPB_F32: return launch_reduce<float, true, true>(p, ws, stream);
-        case SPB_F64: return launch_reduce<double, true, true>(p, ws, stream);
+        case SPB_F32: return launch_spmv_rows<float>(idx, vals, n, ncols, x, y, stream);
+        case SPB_F64: return launch_spmv_rows<double>(idx, vals, n, ncols, x, y, stream);
         default: return SPB_ERR_UNSUPPORTED;
     }
 }

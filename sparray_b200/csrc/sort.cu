@@ -393,6 +393,12 @@ int spb_rekey_sort(int dtype, const int64_t* idx, const void* val, int64_t n, in
 // test), and one compaction pass over the cells emits the touched ones in key order.
 namespace spb {
 
+// A warp reads 32 consecutive elements (coalesced), re-keys them, combines runs of equal new keys with a
+// segmented shuffle scan (when the reduced axis is the last one the elements of an output cell are
+// contiguous; otherwise runs are rare and the scan is a few wasted instructions) and the last lane of
+// each run adds the run's sum into its cell with one float64 atomic.
+constexpr int kAccUnroll = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
                                                               int64_t n, const int64_t* __restrict__ n_dev,
@@ -404,10 +410,41 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
         const int64_t m = *n_dev;
         n = m < n ? m : n;
     }
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t key = apply_rekey(__ldcs(idx + i), rk);
-        atomicAdd(acc + key, (double)__ldcs(val + i));
-        touched[key] = 1;                                      // a flag per cell: explicit zeros survive
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t chunk = 32 * kAccUnroll;
+    for (int64_t base = warp_global * chunk; base < n; base += nwarps * chunk) {
+        int64_t key[kAccUnroll];
+        double v[kAccUnroll];
+#pragma unroll
+        for (int u = 0; u < kAccUnroll; ++u) {
+            const int64_t i = base + u * 32 + lane;
+            key[u] = i < n ? __ldcs(idx + i) : -1;
+            v[u] = i < n ? (double)__ldcs(val + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kAccUnroll; ++u)
+            if (key[u] >= 0) key[u] = apply_rekey(key[u], rk);
+#pragma unroll
+        for (int u = 0; u < kAccUnroll; ++u) {
+            // runs = maximal stretches of ADJACENT lanes with the same key (equal keys further apart are
+            // separate runs and simply cost one more atomic)
+            const int64_t kprev = __shfl_up_sync(0xffffffffu, key[u], 1);
+            const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || kprev != key[u]);
+            const int start = 31 - __clz(heads & ((2u << lane) - 1u));       // first lane of my run
+            double s = v[u];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane - o >= start) s += up;
+            }
+            const bool last = lane == 31 || ((heads >> (lane + 1)) & 1u);
+            if (key[u] >= 0 && last) {
+                atomicAdd(acc + key[u], s);
+                touched[key[u]] = 1;               // a flag per cell: explicit zeros survive
+            }
+        }
     }
 }
 
@@ -492,7 +529,7 @@ static int make_rekey(Rekey& rk, int ndim, const int64_t* in_strides, const int6
 
 static int launch_accumulate(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev,
                              const Rekey& rk, double* acc, uint8_t* touched, cudaStream_t stream) {
-    int64_t blocks = ceil_div(n, 256 * 4);
+    int64_t blocks = ceil_div(n, 256 * kAccUnroll);
     if (blocks > 148 * 16) blocks = 148 * 16;
 #define SPB_ACC(T)                                                                                            \
     SPB_CUDA_TRY(launch_pdl(axis_accumulate_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, idx,   \
