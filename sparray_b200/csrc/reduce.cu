@@ -4,13 +4,13 @@
 //     stream -- the np.unique + np.bincount of FlatSparray.sum(axis) (flat.py:620-625)
 //     and of the non-canonical ctor (flat.py:34-35).  The segment key is
 //     idx / divisor, so sum(axis=last) needs no re-keyed copy of the indices.
+//     One pass, one launch: coalesced loads -> padded shared-memory transpose ->
+//     thread-sequential segmented scan -> block scan -> decoupled look-back that
+//     carries (number of segment heads, open-segment partial sum) across tiles.
 //   * spb_spmv          : y[row] = sum val * x[col] with row = idx / ncols -- the
-//     O(nnz) form of a.dot(x) (flat.py:538-568).
+//     O(nnz) form of a.dot(x) (flat.py:538-568): warp-aggregated float64 atomics,
+//     no shared memory, no look-back.
 //   * spb_min_max, spb_select_flagged.
-//
-// One pass, one launch: coalesced loads -> padded shared-memory transpose ->
-// thread-sequential segmented scan -> block scan -> decoupled look-back that
-// carries (number of segment heads, open-segment partial sum) across tiles.
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -73,7 +73,6 @@ struct ReduceParams {
     const void* vals;
     int64_t n;
     FastDiv div;            // segment key = keys[i] / div.d
-    const void* x;          // MULX: multiply by x[keys[i] - seg * div.d]
     int64_t* out_keys;      // compact output
     double* out_sums;       // compact (or dense: y[seg])
     int64_t* out_count;
@@ -84,7 +83,7 @@ struct ReduceParams {
 // padded position: one spare slot per 8 elements keeps the blocked reads conflict-free
 __device__ __forceinline__ int pad8(int e) { return e + (e >> 3); }
 
-template <typename T, bool MULX, bool DENSE>
+template <typename T>
 __global__ void __launch_bounds__(kRNT, 4) reduce_by_key_kernel(const ReduceParams p) {
     __shared__ int64_t s_key[kRTile + kRTile / 8];
     __shared__ T s_val[kRTile + kRTile / 8];
@@ -132,10 +131,6 @@ __global__ void __launch_bounds__(kRNT, 4) reduce_by_key_kernel(const ReducePara
             const int64_t key = s_key[pad8(first + k)];
             seg[k] = (int64_t)fastdiv((uint64_t)key, p.div);
             double val = (double)s_val[pad8(first + k)];
-            if constexpr (MULX) {
-                const int64_t col = key - seg[k] * (int64_t)p.div.d;
-                val *= (double)__ldg(reinterpret_cast<const T*>(p.x) + col);
-            }
             v[k] = val;
         }
     }
@@ -201,27 +196,6 @@ __global__ void __launch_bounds__(kRNT, 4) reduce_by_key_kernel(const ReducePara
     if (lane == 0) lane_excl = Carry{0, 0.0, false};
     Carry excl = combine(wpre, lane_excl);      // everything in this tile before my first item
 
-    if constexpr (DENSE) {
-        // Dense output (SpMV): no output compaction, so no cross-tile look-back at all.  A row that is
-        // wholly inside this tile is stored; the pieces of a row that crosses a tile border are added
-        // atomically into the zero-initialised y (at most two such rows per tile).
-        double* y = p.out_sums;
-#pragma unroll
-        for (int k = 0; k < kRVT; ++k) {
-            if (k < cnt) {
-                const bool tile_last = first + k == tile_items - 1;
-                const int64_t nxt = (k + 1 < cnt) ? seg[k + 1] : after;
-                if (nxt != seg[k] || tile_last) {
-                    const bool inside_start = (head_bits & ((2u << k) - 1u)) != 0 || excl.flag;
-                    const bool continues = tile_last && after == seg[k];
-                    const double total = (head_bits & ((2u << k) - 1u)) ? incl[k] : excl.val + incl[k];
-                    if (inside_start && !continues) y[seg[k]] = total;
-                    else atomicAdd(&y[seg[k]], total);
-                }
-            }
-        }
-        return;
-    }
     // ---- decoupled look-back (warp 0) ----------------------------------------------------------
     if (warp == 0) {
         int64_t heads_before = 0;
@@ -269,7 +243,7 @@ __global__ void __launch_bounds__(kRNT, 4) reduce_by_key_kernel(const ReducePara
                      incl_prefix.val);
             s_tile_heads = heads_before;
             s_tile_carry = carry;
-            if (!DENSE && tile_start + tile_items == p.n) *p.out_count = incl_prefix.heads;
+            if (tile_start + tile_items == p.n) *p.out_count = incl_prefix.heads;
         }
     }
     __syncthreads();
@@ -285,13 +259,12 @@ __global__ void __launch_bounds__(kRNT, 4) reduce_by_key_kernel(const ReducePara
             if (head_bits & (1u << k)) {
                 ++pos;
                 seen_head = true;
-                if constexpr (!DENSE) p.out_keys[pos] = seg[k];
+                p.out_keys[pos] = seg[k];
             }
             const int64_t nxt = (k + 1 < cnt) ? seg[k + 1] : after;
             if (nxt != seg[k]) {   // segment ends here
                 const double total = seen_head ? incl[k] : carry_in + incl[k];
-                if constexpr (DENSE) p.out_sums[seg[k]] = total;
-                else p.out_sums[pos] = total;
+                p.out_sums[pos] = total;
             }
         }
     }
@@ -385,7 +358,7 @@ __global__ void __launch_bounds__(256) select_flagged_kernel(const int64_t* __re
     }
 }
 
-template <typename T, bool MULX, bool DENSE>
+template <typename T>
 int launch_reduce(ReduceParams& p, spb_workspace* ws, cudaStream_t stream) {
     const int64_t ntiles = ceil_div(p.n, kRTile);
     if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
@@ -399,12 +372,12 @@ int launch_reduce(ReduceParams& p, spb_workspace* ws, cudaStream_t stream) {
     {
         static bool configured = false;
         if (!configured) {   // let the SM give this kernel all the shared memory it can use
-            SPB_CUDA_TRY(cudaFuncSetAttribute(reduce_by_key_kernel<T, MULX, DENSE>,
+            SPB_CUDA_TRY(cudaFuncSetAttribute(reduce_by_key_kernel<T>,
                                               cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             configured = true;
         }
     }
-    reduce_by_key_kernel<T, MULX, DENSE><<<(unsigned)ntiles, kRNT, 0, stream>>>(p);
+    reduce_by_key_kernel<T><<<(unsigned)ntiles, kRNT, 0, stream>>>(p);
     SPB_LAUNCHED(1);
     return (int)cudaGetLastError();
 }
@@ -424,7 +397,7 @@ int spb_reduce_by_key(int dtype, const int64_t* keys, const void* vals, int64_t 
     ReduceParams p{};
     p.keys = keys; p.vals = vals; p.n = n; p.div = make_fastdiv((uint64_t)key_divisor);
     p.out_keys = out_keys; p.out_sums = out_sums; p.out_count = out_count;
-#define SPB_RBK(T) return launch_reduce<T, false, false>(p, ws, stream)
+#define SPB_RBK(T) return launch_reduce<T>(p, ws, stream)
     switch (dtype) {
         case SPB_F32: SPB_RBK(float);
         case SPB_F64: SPB_RBK(double);
