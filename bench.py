@@ -43,9 +43,9 @@ DTYPE = np.float32
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # ncu --set full capture of this workload (profiles/README.md); None until a capture exists
-NCU_TRAFFIC_BYTES = 200181504   # 195.63 MB read + 4.55 MB written
+NCU_TRAFFIC_BYTES = 201019136   # 195.90 MB read + 5.12 MB written
 NCU_TRAFFIC_SOURCE = ("profiles/r1_setop_intersect_final_ncu_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum of "
-                      "setop_kernel<float,float,INTERSECT> (74 % of the call's GPU time; the partition and reorder "
+                      "setop_kernel<float,float,INTERSECT> (69 % of the call's GPU time; the partition and reorder "
                       "launches were not captured with --set full)")
 
 
