@@ -327,6 +327,11 @@ def main():
     if world == 1 and not args.no_ops:
         ops = op_breakdown(sp, torch, A, B, peak)
 
+    # ---- sharded exchange step (N>1 only; not the headline): operands with MISALIGNED splitters ------
+    sharded = None
+    if world > 1 and not args.no_ops:
+        sharded = sharded_exchange(torch, dist, A, B, rank, world, barrier, max_over_ranks)
+
     # ---- CPU baseline beside it (rank 0, N=1) ---------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1:
@@ -366,6 +371,8 @@ def main():
         }
         if ops is not None:
             out["ops"] = ops
+        if sharded is not None:
+            out["sharded_exchange"] = sharded
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -398,6 +405,53 @@ def synth_sorted(torch, n, size, dtype, seed):
     idx = idx[idx < size]
     val = torch.randn(idx.numel(), device="cuda", generator=g, dtype=dtype)
     return idx.contiguous(), val
+
+
+def sharded_exchange(torch, dist, A, B, rank, world, barrier, max_over_ranks):
+    """SURVEY.md section 8(e), the one real exchange step of a binop: b arrives range-partitioned with
+    splitters shifted by half a shard, so `a * b` first repartitions b -- counts all-gather + one
+    variable-size all-to-all over NVLink in which every rank ships half of its shard to a neighbour --
+    and then runs the local fused intersection.  Device-timed, max over ranks."""
+    from sparray_b200 import sharded as sh
+    size = int(np.prod(SHAPE))
+    gshape = (SHAPE[0] * world,) + tuple(SHAPE[1:])
+    even = [r * size for r in range(world + 1)]
+    shifted = [0] + [r * size + size // 2 for r in range(world - 1)] + [world * size]     # rank 0 owns half a shard
+    a_sh = sh.ShardedFlatSparray(A.indices + rank * size, A.data, gshape, even)
+    # build b on the shifted partition: take it from the even one with a (untimed) repartition
+    b_even = sh.ShardedFlatSparray(B.indices + rank * size, B.data, gshape, even)
+    b_sh = b_even.repartition(shifted)
+    moved = b_sh.repartition(even)                  # warm-up of the timed exchange (allocator, NCCL channels)
+    n_moved_local = int(b_sh.nnz_local)
+    del moved
+
+    def timed(fn, reps=5):
+        ts = []
+        for _ in range(reps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(max_over_ranks(e0.elapsed_time(e1)))
+            del r
+        return float(np.median(ts))
+    t_rep = timed(lambda: b_sh.repartition(even))
+    t_mul = timed(lambda: (a_sh * b_sh).nnz_local)          # repartition + local fused intersection
+    # bytes a rank SENDS in the exchange: the elements of its shifted shard that belong to another rank
+    sent = int(((b_sh.indices < rank * size) | (b_sh.indices >= (rank + 1) * size)).sum().item())
+    tot = torch.tensor([sent, n_moved_local], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tot)
+    sent_all, n_all = int(tot[0].item()), int(tot[1].item())
+    bytes_per_elem = 8 + B.data.element_size()
+    return {"what": "b range-partitioned with splitters shifted by half a shard; a*b = repartition(b) + local intersection",
+            "repartition_ms": t_rep, "mul_with_repartition_ms": t_mul, "elements_repartitioned": n_all,
+            "elements_crossing_gpus": sent_all,
+            "nvlink_GBps_per_gpu_send": sent_all / world * bytes_per_elem / (t_rep * 1e-3) / 1e9,
+            "nvlink_peak_GBps_per_direction": 900.0,
+            "note": "repartition = lower_bound of the splitters, counts all-gather (host sync), index and value "
+                    "all_to_all_single (NCCL); received segments are already in order, no merge"}
 
 
 def op_breakdown(sp, torch, A, B, peak):

@@ -175,7 +175,7 @@ class ShardedFlatSparray:
         counts = torch.tensor(send_counts, dtype=torch.int64, device=dev)
         all_counts = [torch.empty_like(counts) for _ in range(self.world)]
         dist.all_gather(all_counts, counts, group=self.group)
-        recv_counts = [int(all_counts[s][self.rank].item()) for s in range(self.world)]
+        recv_counts = torch.stack(all_counts)[:, self.rank].cpu().tolist()      # one read-back, not one per source
         lo = cut[0]
         send_idx = self.indices[lo:cut[-1]].contiguous()
         send_val = self.data[lo:cut[-1]].contiguous()
