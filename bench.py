@@ -197,6 +197,18 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: sparray_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # one process per GPU share the host cores: give every rank its own slice so that the Python that
+        # enqueues the steps is not migrated or preempted by another rank's (the step is ~60 us of host
+        # work against ~80 us of device work, so host jitter shows up in the max over ranks)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(len(cores) // world, 1)
+            mine = cores[(local_rank * per) % len(cores):][:per]
+            if mine:
+                os.sched_setaffinity(0, set(mine))
+        except (AttributeError, OSError):
+            pass
+    if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import sparray_b200 as sp

@@ -19,4 +19,4 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(200): step()
 torch.cuda.synchronize()
 pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+pstats.Stats(pr).sort_stats("tottime").print_stats(22)
