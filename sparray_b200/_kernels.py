@@ -2,6 +2,7 @@
 streams are torch's job), call the C ABI (include/sparray_b200.h), trim to the
 device-side count.  No arithmetic happens in Python or in torch ops here."""
 import ctypes
+import functools
 
 import numpy as np
 import torch
@@ -316,6 +317,16 @@ def sum_axis(idx, val, shape, axis, n_dev=None):
     return reduce_by_key(keys, vals, 1) + (None,)
 
 
+@functools.lru_cache(maxsize=512)
+def _stride_args(in_strides, out_strides):
+    """(ndim, void* in, void* out) of two stride tuples as host int64 arrays; the arrays are kept alive
+    by the cache entry (the C side reads them during the call only)."""
+    ndim = len(in_strides)
+    ins = (ctypes.c_int64 * ndim)(*in_strides)
+    outs = (ctypes.c_int64 * ndim)(*out_strides)
+    return ndim, ctypes.cast(ins, ctypes.c_void_p), ctypes.cast(outs, ctypes.c_void_p), (ins, outs)
+
+
 def axis_sum_dense(idx, val, in_strides, out_strides, cells, n_dev=None):
     require_cuda()
     n = idx.numel()
@@ -323,11 +334,8 @@ def axis_sum_dense(idx, val, in_strides, out_strides, cells, n_dev=None):
     out_idx = torch.empty(cap, dtype=torch.int64, device=idx.device)
     out_sums = torch.empty(cap, dtype=torch.float64, device=idx.device)
     cnt = torch.empty(1, dtype=torch.int64, device=idx.device)
-    ndim = len(in_strides)
-    ins = (ctypes.c_int64 * ndim)(*in_strides)
-    outs = (ctypes.c_int64 * ndim)(*out_strides)
-    check(lib.spb_axis_sum_dense(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), n, ptr(n_dev), ndim,
-                                 ctypes.cast(ins, ctypes.c_void_p), ctypes.cast(outs, ctypes.c_void_p), int(cells),
+    ndim, ins, outs, _keep = _stride_args(tuple(in_strides), tuple(out_strides))
+    check(lib.spb_axis_sum_dense(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), n, ptr(n_dev), ndim, ins, outs, int(cells),
                                  ptr(out_idx), ptr(out_sums), ptr(cnt), workspace(), stream()))
     return out_idx, out_sums, cnt
 
@@ -339,11 +347,8 @@ def axis_accumulate(idx, val, in_strides, out_strides, cells):
     cells = int(cells)
     acc = torch.zeros(cells, dtype=torch.float64, device=idx.device)
     touched = torch.zeros((cells + 63) // 64 * 64, dtype=torch.uint8, device=idx.device)
-    ndim = len(in_strides)
-    ins = (ctypes.c_int64 * ndim)(*in_strides)
-    outs = (ctypes.c_int64 * ndim)(*out_strides)
-    check(lib.spb_axis_accumulate(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), idx.numel(), ndim,
-                                  ctypes.cast(ins, ctypes.c_void_p), ctypes.cast(outs, ctypes.c_void_p), cells,
+    ndim, ins, outs, _keep = _stride_args(tuple(in_strides), tuple(out_strides))
+    check(lib.spb_axis_accumulate(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), idx.numel(), ndim, ins, outs, cells,
                                   ptr(acc), ptr(touched), stream()))
     return acc, touched
 

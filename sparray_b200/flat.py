@@ -116,7 +116,7 @@ class FlatSparray(_BaseSparray):
         if cnt is None:
             return cls(idx, val, shape=shape, is_canonical=True)
         self = cls.__new__(cls)
-        self.shape = tuple(int(s) for s in shape)
+        self.shape = shape if type(shape) is tuple else tuple(int(s) for s in shape)   # callers pass self.shape slices
         self._pending = (idx, val, cnt)
         self._indices = self._data = None
         return self
