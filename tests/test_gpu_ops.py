@@ -464,3 +464,30 @@ def test_axis_accumulate_and_emit_ranges(sp):
         np.testing.assert_array_equal(got_i, wi)
         np.testing.assert_allclose(got_v, wv, rtol=1e-5, atol=1e-6 * np.abs(wv).max())
         assert float(acc.abs().sum().item()) == 0.0 and int(touched.sum().item()) == 0    # emitted cells were zeroed
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_sum_and_dot_small_shapes_fuzz(sp, seed):
+    """Tiny shapes, dense-ish arrays: inside one warp the same output cell is hit by many elements that
+    are NOT adjacent (the warp-aggregated atomics must treat them as separate runs), rows shorter and
+    longer than a warp, every axis, several dtypes -- against the oracle."""
+    rng = np.random.default_rng(100 + seed)
+    ndim = int(rng.integers(2, 5))
+    shape = tuple(int(x) for x in rng.integers(2, 9, ndim))
+    size = int(np.prod(shape))
+    nnz = int(rng.integers(1, size + 1))
+    dtype = [np.float64, np.float32, np.int32, np.int64][seed % 4]
+    idx = np.sort(rng.choice(size, nnz, replace=False)).astype(np.int64)
+    val = rng.integers(-5, 6, nnz).astype(dtype) if np.dtype(dtype).kind == "i" else rng.standard_normal(nnz).astype(dtype)
+    A = sp.FlatSparray(idx, val, shape=shape, is_canonical=True)
+    for axis in range(ndim):
+        wi, wv, wshape = fo.sum_axis(idx, val, shape, axis)
+        got = A.sum(axis=axis)
+        assert got.shape == tuple(wshape)
+        assert_sparse_same(got, (wi, wv, tuple(wshape)), exact=False, rtol=1e-5 if dtype == np.float32 else 1e-12)
+    if np.dtype(dtype).kind == "f":
+        x = rng.standard_normal(shape[-1]).astype(dtype)
+        want = fo.dot_dense_vector(idx, val, shape, x)
+        got = A.dot(x)
+        np.testing.assert_allclose(np.asarray(got, dtype=np.float64), want, rtol=1e-5 if dtype == np.float32 else 1e-12,
+                                   atol=(1e-5 if dtype == np.float32 else 1e-12) * max(np.abs(want).max(), 1.0))
