@@ -451,6 +451,15 @@ def sharded_exchange(torch, dist, A, B, rank, world, barrier, max_over_ranks):
         return float(np.median(ts))
     t_rep = timed(lambda: b_sh.repartition(even))
     t_mul = timed(lambda: (a_sh * b_sh).nnz_local)          # repartition + local fused intersection
+    # the same product with no exchange step: b's shards published in symmetric memory (untimed, once per
+    # operand), the merge kernels read the partner's slices over NVLink inside their TMA staging
+    b_pub = b_sh.publish()
+    want = (a_sh * b_sh)
+    got = a_sh.binop_peer(b_pub, "intersect", "mul")
+    assert got.nnz_local == want.nnz_local and bool((got.indices == want.indices).all()) and bool((got.data == want.data).all())
+    del want, got
+    t_peer = timed(lambda: a_sh.binop_peer(b_pub, "intersect", "mul").nnz_local)
+    b_pub.barrier()
     # bytes a rank SENDS in the exchange: the elements of its shifted shard that belong to another rank
     sent = int(((b_sh.indices < rank * size) | (b_sh.indices >= (rank + 1) * size)).sum().item())
     tot = torch.tensor([sent, n_moved_local], dtype=torch.int64, device="cuda")
@@ -458,12 +467,15 @@ def sharded_exchange(torch, dist, A, B, rank, world, barrier, max_over_ranks):
     sent_all, n_all = int(tot[0].item()), int(tot[1].item())
     bytes_per_elem = 8 + B.data.element_size()
     return {"what": "b range-partitioned with splitters shifted by half a shard; a*b = repartition(b) + local intersection",
-            "repartition_ms": t_rep, "mul_with_repartition_ms": t_mul, "elements_repartitioned": n_all,
+            "repartition_ms": t_rep, "mul_with_repartition_ms": t_mul, "mul_with_peer_loads_ms": t_peer,
+            "elements_repartitioned": n_all,
             "elements_crossing_gpus": sent_all,
             "nvlink_GBps_per_gpu_send": sent_all / world * bytes_per_elem / (t_rep * 1e-3) / 1e9,
             "nvlink_peak_GBps_per_direction": 900.0,
             "note": "repartition = lower_bound of the splitters, counts all-gather (host sync), index and value "
-                    "all_to_all_single (NCCL); received segments are already in order, no merge"}
+                    "all_to_all_single (NCCL); received segments are already in order, no merge.  peer loads = "
+                    "ShardedFlatSparray.binop_peer: one all-gather of cut positions, then one fused merge launch "
+                    "per overlapping source rank reading that rank's slice from symmetric memory over NVLink"}
 
 
 def op_breakdown(sp, torch, A, B, peak):

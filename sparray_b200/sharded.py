@@ -13,6 +13,11 @@ run on it unchanged.
     destination is a contiguous slice (found by a batched binary search of the splitters),
     and because the source partition is itself a range partition, concatenating the
     received segments in source-rank order is already globally sorted: no merge, no sort;
+  * misaligned operands, second form (``publish`` + ``binop_peer``): the partner's shards live in
+    symmetric memory (``torch.distributed._symmetric_memory``), every GPU maps every peer's copy, and
+    the fused merge kernels READ THE PARTNER'S SLICES OVER NVLINK inside their TMA staging -- the
+    exchange and the merge are one kernel, nothing is repartitioned, no intermediate buffer exists;
+    the only collective is one tiny all-gather of cut positions;
   * axis sums: local segmented reduce; only output keys on a shard border can collide, so
     the borders are fixed by an allgather of one (key, value) pair per rank -- or, when the
     reduced axis is not the last one, an all-to-all of the partial sums by output-key range
@@ -164,6 +169,50 @@ class ShardedFlatSparray:
     def maximum(self, other):
         return self._binop(other, "union", "maximum")
 
+    # ---- misaligned operands without an exchange step: read the partner over NVLink ---------------------
+    def publish(self):
+        """Copy this shard into symmetric memory and map every peer's copy (collective; do it once for
+        an operand that will be the misaligned partner of several ops)."""
+        return PeerShards(self)
+
+    def binop_peer(self, other, kind, op):
+        """``self (op) other`` where ``other`` is a published, differently partitioned operand: for
+        every source rank whose key range overlaps mine, ONE fused merge launch whose B operand is a
+        slice of that rank's shard read straight from its memory (TMA bulk copies over NVLink).  The
+        result is partitioned like ``self``.  Collectives: one all-gather of (world + 1) cut positions."""
+        assert isinstance(other, PeerShards) and other.shape == self.shape
+        dev = self.indices.device
+        lo, hi = self.splitters[self.rank], self.splitters[self.rank + 1]
+        # where my key range [lo, hi) starts and ends inside EVERY rank's shard of `other`: each rank
+        # cuts its own shard at all my-partition splitters, one all-gather shares the cuts
+        mine = torch.tensor(self.splitters, dtype=torch.int64, device=dev)
+        cuts = self.ops.lower_bound(other.local_indices(), mine)                       # [world + 1]
+        all_cuts = torch.empty(self.world * (self.world + 1), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_cuts, cuts.contiguous(), group=self.group)
+        # my own elements, cut at the partner's splitters (clipped to my range): piece s meets source s
+        theirs = torch.tensor([min(max(x, lo), hi) for x in other.splitters], dtype=torch.int64, device=dev)
+        a_cuts = self.ops.lower_bound(self.indices, theirs)
+        host = torch.cat([all_cuts, a_cuts]).cpu().tolist()                           # the one read-back
+        all_cuts, a_cuts = host[:self.world * (self.world + 1)], host[self.world * (self.world + 1):]
+        out_i, out_v = [], []
+        for s in range(self.world):
+            c0 = all_cuts[s * (self.world + 1) + self.rank]
+            c1 = all_cuts[s * (self.world + 1) + self.rank + 1]
+            a0, a1 = a_cuts[s], a_cuts[s + 1]
+            if kind == "intersect" and (c1 == c0 or a1 == a0):
+                continue
+            if c1 == c0 and a1 == a0:
+                continue
+            b_idx, b_val = other.slice_of(s, c0, c1)
+            i, v = self.ops.binop(kind, op, self.indices[a0:a1], self.data[a0:a1], b_idx, b_val)
+            out_i.append(i)
+            out_v.append(v)
+        if not out_i:
+            i, v = self.ops.binop(kind, op, self.indices[:0], self.data[:0], self.indices[:0], other.local_values()[:0])
+            return self._like(i, v)
+        return self._like(torch.cat(out_i) if len(out_i) > 1 else out_i[0],
+                          torch.cat(out_v) if len(out_v) > 1 else out_v[0])
+
     # ---- repartition: counts allgather + one variable-size all-to-all --------------------------------
     def repartition(self, new_splitters):
         new_splitters = [int(s) for s in new_splitters]
@@ -306,6 +355,50 @@ class ShardedFlatSparray:
         idx = np.concatenate([gi[r][:ns[r]].cpu().numpy() for r in range(self.world)])
         val = np.concatenate([gv[r][:ns[r]].cpu().numpy() for r in range(self.world)])
         return idx, val
+
+
+class PeerShards:
+    """A range-sharded operand whose shards live in symmetric memory: every rank can hand slices of
+    ANY rank's shard to a local kernel as ordinary device pointers (peer mappings over NVLink /
+    NVSwitch).  The buffers must not be modified while peers may still be reading them: ``barrier()``
+    before dropping or rewriting."""
+
+    def __init__(self, sharded):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.shape, self.splitters = sharded.shape, list(sharded.splitters)
+        self.group, self.rank, self.world = sharded.group, sharded.rank, sharded.world
+        dev = sharded.indices.device
+        n = torch.tensor([sharded.nnz_local], dtype=torch.int64, device=dev)
+        dist.all_reduce(n, op=dist.ReduceOp.MAX, group=self.group)
+        cap = max(int(n.item()), 1)                               # symmetric: the same size on every rank
+        self.n_local = sharded.nnz_local
+        self.dtype = sharded.data.dtype
+        self._idx = symm_mem.empty(cap, dtype=torch.int64, device=dev)
+        self._val = symm_mem.empty(cap, dtype=self.dtype, device=dev)
+        self._idx[:self.n_local].copy_(sharded.indices)
+        self._val[:self.n_local].copy_(sharded.data)
+        name = (self.group or dist.group.WORLD).group_name
+        self._h_idx = symm_mem.rendezvous(self._idx, name)
+        self._h_val = symm_mem.rendezvous(self._val, name)
+        self.barrier()
+
+    def barrier(self):
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(group=self.group)
+
+    def local_indices(self):
+        return self._idx[:self.n_local]
+
+    def local_values(self):
+        return self._val[:self.n_local]
+
+    def slice_of(self, src, c0, c1):
+        """(indices, values) of elements [c0, c1) of rank ``src``'s shard, as tensors over peer memory."""
+        n = int(c1 - c0)
+        if src == self.rank or n == 0:
+            return self._idx[c0:c0 + n], self._val[c0:c0 + n]
+        return (self._h_idx.get_buffer(src, (n,), torch.int64, storage_offset=int(c0)),
+                self._h_val.get_buffer(src, (n,), self.dtype, storage_offset=int(c0)))
 
 
 def _exchange_unsorted(part, out_split):

@@ -51,6 +51,14 @@ def main():
     same(A - B, fo.pairwise_union(ai, av, bi, -bv, np.add))
     A2 = A.repartition(sp)
     same(A2 + B, fo.pairwise_union(ai, av, bi, bv, np.add))
+    # the same misaligned binops with NO exchange step: B's shards in symmetric memory, the merge
+    # kernels read the partner's slices over NVLink
+    Bp = B.publish()
+    for X in (A, A2):
+        same(X.binop_peer(Bp, "union", "add"), fo.pairwise_union(ai, av, bi, bv, np.add))
+        same(X.binop_peer(Bp, "intersect", "mul"), fo.pairwise_intersect(ai, av, bi, bv, np.multiply))
+        same(X.binop_peer(Bp, "union", "sub"), fo.pairwise_union(ai, av, bi, -bv, np.add))
+    Bp.barrier()
     for axis in range(4):
         same(A2.sum(axis), fo.sum_axis(ai, av, shape, axis)[:2], exact=False)
     for axes in ((3, 2, 1, 0), (2, 0, 3, 1)):
