@@ -53,6 +53,15 @@ class CudaOps:
             b_val = self.k.cast(b_val, common) if b_val.dtype != common else b_val
         return self.k.setop_binop(kind, op, a_idx, a_val, b_idx, b_val)[:2]
 
+    def binop_lazy(self, kind, op, a_idx, a_val, b_idx, b_val):
+        """(worst-case-sized indices, values, device count or None): no host synchronisation."""
+        from . import _dtypes as dt
+        if a_val.dtype != b_val.dtype:
+            common = dt.promote(a_val.dtype, b_val.dtype)
+            a_val = self.k.cast(a_val, common) if a_val.dtype != common else a_val
+            b_val = self.k.cast(b_val, common) if b_val.dtype != common else b_val
+        return self.k.setop_binop(kind, op, a_idx, a_val, b_idx, b_val, lazy=True)
+
     def reduce_by_key(self, keys, vals, divisor=1):
         return self.k.reduce_by_key(keys, vals, divisor)
 
@@ -194,7 +203,8 @@ class ShardedFlatSparray:
         a_cuts = self.ops.lower_bound(self.indices, theirs)
         host = torch.cat([all_cuts, a_cuts]).cpu().tolist()                           # the one read-back
         all_cuts, a_cuts = host[:self.world * (self.world + 1)], host[self.world * (self.world + 1):]
-        out_i, out_v = [], []
+        # all launches first (their element counts stay on the device), then ONE read-back of the counts
+        pieces = []
         for s in range(self.world):
             c0 = all_cuts[s * (self.world + 1) + self.rank]
             c1 = all_cuts[s * (self.world + 1) + self.rank + 1]
@@ -204,14 +214,20 @@ class ShardedFlatSparray:
             if c1 == c0 and a1 == a0:
                 continue
             b_idx, b_val = other.slice_of(s, c0, c1)
-            i, v = self.ops.binop(kind, op, self.indices[a0:a1], self.data[a0:a1], b_idx, b_val)
-            out_i.append(i)
-            out_v.append(v)
-        if not out_i:
+            pieces.append(self.ops.binop_lazy(kind, op, self.indices[a0:a1], self.data[a0:a1], b_idx, b_val))
+        if not pieces:
             i, v = self.ops.binop(kind, op, self.indices[:0], self.data[:0], self.indices[:0], other.local_values()[:0])
             return self._like(i, v)
-        return self._like(torch.cat(out_i) if len(out_i) > 1 else out_i[0],
-                          torch.cat(out_v) if len(out_v) > 1 else out_v[0])
+        pending = [p[2] for p in pieces if p[2] is not None]
+        counts = torch.cat(pending).cpu().tolist() if pending else []
+        out_i, out_v, j = [], [], 0
+        for i, v, c in pieces:
+            if c is not None:
+                i, v = i[:counts[j]], v[:counts[j]]
+                j += 1
+            out_i.append(i)
+            out_v.append(v)
+        return self._like(torch.cat(out_i), torch.cat(out_v))
 
     # ---- repartition: counts allgather + one variable-size all-to-all --------------------------------
     def repartition(self, new_splitters):
