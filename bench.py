@@ -210,7 +210,9 @@ def main():
             pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
     import sparray_b200 as sp
     from sparray_b200 import _dtypes as dt
     from sparray_b200._lib import check, lib, ptr, stream, workspace
@@ -342,7 +344,10 @@ def main():
     # ---- sharded exchange step (N>1 only; not the headline): operands with MISALIGNED splitters ------
     sharded = None
     if world > 1 and not args.no_ops:
-        sharded = sharded_exchange(torch, dist, A, B, rank, world, barrier, max_over_ranks)
+        try:
+            sharded = sharded_exchange(torch, dist, A, B, rank, world, barrier, max_over_ranks)
+        except Exception as exc:  # never let the side measurement take the headline line down
+            sharded = {"error": str(exc).splitlines()[0][:300]}
 
     # ---- CPU baseline beside it (rank 0, N=1) ---------------------------------------------------------
     cpu = None
@@ -453,13 +458,21 @@ def sharded_exchange(torch, dist, A, B, rank, world, barrier, max_over_ranks):
     t_mul = timed(lambda: (a_sh * b_sh).nnz_local)          # repartition + local fused intersection
     # the same product with no exchange step: b's shards published in symmetric memory (untimed, once per
     # operand), the merge kernels read the partner's slices over NVLink inside their TMA staging
-    b_pub = b_sh.publish()
-    want = (a_sh * b_sh)
-    got = a_sh.binop_peer(b_pub, "intersect", "mul")
-    assert got.nnz_local == want.nnz_local and bool((got.indices == want.indices).all()) and bool((got.data == want.data).all())
-    del want, got
-    t_peer = timed(lambda: a_sh.binop_peer(b_pub, "intersect", "mul").nnz_local)
-    b_pub.barrier()
+    t_peer, peer_note = None, "ok"
+    try:
+        b_pub = b_sh.publish()
+        want = (a_sh * b_sh)
+        got = a_sh.binop_peer(b_pub, "intersect", "mul")
+        same = got.nnz_local == want.nnz_local and bool((got.indices == want.indices).all()) and \
+            bool((got.data == want.data).all())
+        del want, got
+        if same:
+            t_peer = timed(lambda: a_sh.binop_peer(b_pub, "intersect", "mul").nnz_local)
+        else:
+            peer_note = "MISMATCH against the repartition path"
+        b_pub.barrier()
+    except Exception as exc:      # symmetric memory unavailable on this box: the NCCL path above still stands
+        peer_note = "unavailable: %s" % str(exc).splitlines()[0][:200]
     # bytes a rank SENDS in the exchange: the elements of its shifted shard that belong to another rank
     sent = int(((b_sh.indices < rank * size) | (b_sh.indices >= (rank + 1) * size)).sum().item())
     tot = torch.tensor([sent, n_moved_local], dtype=torch.int64, device="cuda")
@@ -467,7 +480,7 @@ def sharded_exchange(torch, dist, A, B, rank, world, barrier, max_over_ranks):
     sent_all, n_all = int(tot[0].item()), int(tot[1].item())
     bytes_per_elem = 8 + B.data.element_size()
     return {"what": "b range-partitioned with splitters shifted by half a shard; a*b = repartition(b) + local intersection",
-            "repartition_ms": t_rep, "mul_with_repartition_ms": t_mul, "mul_with_peer_loads_ms": t_peer,
+            "repartition_ms": t_rep, "mul_with_repartition_ms": t_mul, "mul_with_peer_loads_ms": t_peer, "peer_loads_status": peer_note,
             "elements_repartitioned": n_all,
             "elements_crossing_gpus": sent_all,
             "nvlink_GBps_per_gpu_send": sent_all / world * bytes_per_elem / (t_rep * 1e-3) / 1e9,
