@@ -491,3 +491,27 @@ def test_sum_and_dot_small_shapes_fuzz(sp, seed):
         got = A.dot(x)
         np.testing.assert_allclose(np.asarray(got, dtype=np.float64), want, rtol=1e-5 if dtype == np.float32 else 1e-12,
                                    atol=(1e-5 if dtype == np.float32 else 1e-12) * max(np.abs(want).max(), 1.0))
+
+
+def test_lazily_counted_chain_every_axis(sp):
+    """(a * b) and (a + b) are lazily counted (their element counts stay on the device); sum(axis)
+    consumes the pending count without resolving it.  Every axis, and the results themselves."""
+    rng = np.random.default_rng(21)
+    shape = (48, 40, 36, 16)
+    ai, av = rand_operand(rng, shape, 150000, np.float32)
+    bi, bv = rand_operand(rng, shape, 140000, np.float32)
+    A = sp.FlatSparray(ai, av, shape=shape, is_canonical=True)
+    B = sp.FlatSparray(bi, bv, shape=shape, is_canonical=True)
+    ci, cv = fo.pairwise_intersect(ai, av, bi, bv, np.multiply)
+    ui, uv = fo.pairwise_union(ai, av, bi, bv, np.add)
+    for axis in range(4):
+        C = A * B
+        assert C._pending is not None                       # not resolved by the product itself
+        S = C.sum(axis=axis)
+        assert C._pending is not None, "sum(axis) must not force the count read-back"
+        assert_sparse_same(S, fo.sum_axis(ci, cv, shape, axis), exact=False, rtol=1e-5)
+        U = A + B
+        assert_sparse_same(U.sum(axis=axis), fo.sum_axis(ui, uv, shape, axis), exact=False, rtol=1e-5)
+    C = A * B
+    assert_sparse_same(C, (ci, cv, shape))
+    assert C._pending is None and C.nnz == len(ci)
