@@ -448,6 +448,96 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
     }
 }
 
+// Variant for LONG runs (reduced axis innermost and many elements per output cell): a lane owns kAccItems
+// CONSECUTIVE elements (one or two sectors), a warp 128.  The lane re-keys its
+// elements and adds up those that fall into the same cell as its first one as long as they are adjacent
+// (when the reduced axis is the last one the elements of a cell are contiguous, so a lane usually holds
+// ONE run); a lane holding a single run hands (cell, sum) to one segmented shuffle scan per 128 elements,
+// whose run ends issue one float64 atomic each; a lane holding several runs adds its pieces atomically
+// on its own.
+constexpr int kAccItems = 4;
+
+__device__ __forceinline__ double warp_run_sum(int64_t cell, double s, int lane, bool& last) {
+    const int64_t cprev = __shfl_up_sync(0xffffffffu, cell, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || cprev != cell || cell < 0);
+    const int start = 31 - __clz(heads & ((2u << lane) - 1u));       // first lane of my run
+    if (heads != 0xffffffffu) {                                       // some run is longer than one lane
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane - o >= start) s += up;
+        }
+    }
+    last = lane == 31 || ((heads >> (lane + 1)) & 1u);
+    return s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) axis_accumulate_runs_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
+                                                              int64_t n, const int64_t* __restrict__ n_dev,
+                                                              const Rekey rk, double* __restrict__ acc,
+                                                              uint8_t* __restrict__ touched) {
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();   // operands (and n_dev) may come from the previous launch
+    if (n_dev) {                       // the producer's count never left the device; n is its upper bound
+        const int64_t m = *n_dev;
+        n = m < n ? m : n;
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t chunk = 32 * kAccItems;
+    for (int64_t base = warp_global * chunk; base < n; base += nwarps * chunk) {
+        const int64_t i0 = base + (int64_t)lane * kAccItems;
+        int64_t key[kAccItems];
+        double v[kAccItems];
+#pragma unroll
+        for (int j = 0; j < kAccItems; ++j) {
+            key[j] = i0 + j < n ? __ldcs(idx + i0 + j) : -1;
+            v[j] = i0 + j < n ? (double)__ldcs(val + i0 + j) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < kAccItems; ++j)
+            if (key[j] >= 0) key[j] = apply_rekey(key[j], rk);
+        // my runs of adjacent equal cells: all but a single whole-lane run go in atomically right here
+        const bool single = key[0] >= 0 && key[0] == key[1] && key[1] == key[2] && key[2] == key[3];
+        int64_t cell = -2 - lane;      // negative and distinct: takes no part in the warp's runs
+        double s = 0.0;
+        if (single) {
+            cell = key[0];
+            s = (v[0] + v[1]) + (v[2] + v[3]);
+        } else {
+            int64_t run = -1;
+            double rs = 0.0;
+#pragma unroll
+            for (int j = 0; j < kAccItems; ++j) {
+                if (key[j] >= 0) {
+                    if (key[j] != run) {
+                        if (run >= 0) {
+                            atomicAdd(acc + run, rs);
+                            touched[run] = 1;
+                        }
+                        run = key[j];
+                        rs = v[j];
+                    } else {
+                        rs += v[j];
+                    }
+                }
+            }
+            if (run >= 0) {
+                atomicAdd(acc + run, rs);
+                touched[run] = 1;       // a flag per cell: explicit zeros survive
+            }
+        }
+        bool last;
+        s = warp_run_sum(cell, s, lane, last);
+        if (cell >= 0 && last) {
+            atomicAdd(acc + cell, s);
+            touched[cell] = 1;
+        }
+    }
+}
+
 // Emits the touched cells in key order and puts every cell it emitted back to zero, so the
 // accumulator slab is all-zero again when the call is over (no memset per call).  One thread owns
 // 64 cells (four 16-byte loads of flag bytes); a tile of 256 threads covers 16 K cells, which keeps
@@ -528,12 +618,20 @@ static int make_rekey(Rekey& rk, int ndim, const int64_t* in_strides, const int6
 }
 
 static int launch_accumulate(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev,
-                             const Rekey& rk, double* acc, uint8_t* touched, cudaStream_t stream) {
+                             const Rekey& rk, int64_t cells, double* acc, uint8_t* touched, cudaStream_t stream) {
     int64_t blocks = ceil_div(n, 256 * kAccUnroll);
     if (blocks > 148 * 16) blocks = 148 * 16;
+    // long contiguous runs (innermost axis reduced, >= 8 elements per output cell on average): the variant
+    // that pre-reduces inside a lane and scans once per 128 elements
+    const bool long_runs = rk.ndim >= 1 && rk.out_mul[rk.ndim - 1] == 0 && n >= 8 * cells;
 #define SPB_ACC(T)                                                                                            \
-    SPB_CUDA_TRY(launch_pdl(axis_accumulate_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, idx,   \
-                            (const T*)val, n, n_dev, rk, acc, touched));                                      \
+    if (long_runs) {                                                                                          \
+        SPB_CUDA_TRY(launch_pdl(axis_accumulate_runs_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, \
+                                idx, (const T*)val, n, n_dev, rk, acc, touched));                             \
+    } else {                                                                                                  \
+        SPB_CUDA_TRY(launch_pdl(axis_accumulate_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, idx, \
+                                (const T*)val, n, n_dev, rk, acc, touched));                                  \
+    }                                                                                                         \
     break
     switch (dtype) {
         case SPB_F32: SPB_ACC(float);
@@ -586,7 +684,7 @@ extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val
     if (rc) return rc;
     double* const acc = reinterpret_cast<double*>(ws->accum);
     uint8_t* const touched = reinterpret_cast<uint8_t*>(ws->accum) + acc_bytes;
-    rc = launch_accumulate(dtype, idx, val, n, n_dev, rk, acc, touched, stream);
+    rc = launch_accumulate(dtype, idx, val, n, n_dev, rk, cells, acc, touched, stream);
     if (rc) return rc;
     return launch_select(acc, touched, cells, 0, out_idx, out_sums, out_count, ws, stream);
 }
@@ -604,7 +702,7 @@ extern "C" int spb_axis_accumulate(int dtype, const int64_t* idx, const void* va
     if (rc) return rc;
     if (n == 0 || cells == 0) return SPB_OK;
     if (!idx || !val || !acc || !touched) return SPB_ERR_BAD_ARG;
-    return launch_accumulate(dtype, idx, val, n, nullptr, rk, acc, touched, stream);
+    return launch_accumulate(dtype, idx, val, n, nullptr, rk, cells, acc, touched, stream);
 }
 
 // Emit the touched cells of [cell_lo, cell_hi) in key order (keys are absolute cell numbers).
