@@ -296,10 +296,12 @@ def dense_sum_cells(shape, axis):
 
 def sum_axis(idx, val, shape, axis, n_dev=None):
     """(new sorted unique flat indices, float64 sums, device count or None) -- flat.py:617-625.
-    last axis: segmented reduce, no sort; otherwise a dense float64 accumulator when the reduced
-    array is small enough to hold (no sort either), else re-key + radix sort + segmented reduce.
-    The dense path leaves its element count on the device (worst-case-sized outputs); n_dev is the
-    device count of a producer that was not read back either (only valid when dense_sum_cells())."""
+    Whenever the reduced array is small enough to hold densely (and not much sparser than the input):
+    warp-aggregated float64 atomics into a dense accumulator + one compaction pass, no sort, any axis.
+    Otherwise: last axis -> segmented reduce over the already sorted keys; other axes -> re-key +
+    radix sort + segmented reduce.  The dense path leaves its element count on the device
+    (worst-case-sized outputs); n_dev is the device count of a producer that was not read back
+    either (only valid when dense_sum_cells())."""
     from . import _plan
     plan = _plan.axis_sum_plan(shape, axis)
     n = idx.numel()
