@@ -181,3 +181,21 @@ def test_dtype_tables():
     names = [n.strip().split("=")[0].strip() for n in enum.replace("\n", " ").split(",") if n.strip()]
     names = [n for n in names if n != "SPB_UNOP_COUNT"]
     assert [n[len("SPB_U_"):].lower() for n in names] == sorted(dt.UNOPS, key=dt.UNOPS.get)
+
+
+def test_dense_sum_eligibility_and_cached_plans():
+    """Host-side decisions of sum(axis): which shapes may consume a pending (device-side) count, and
+    that the cached plans are the plain ones."""
+    from sparray_b200 import _kernels as k, _plan
+    assert k.dense_sum_cells((256, 256, 256, 64), 2) == 256 * 256 * 64          # 4.2 M cells: dense whatever nnz is
+    assert k.dense_sum_cells((256, 256, 256, 64), 3) == 0                       # 16.7 M cells: needs the real count
+    assert k.dense_sum_cells((10 ** 6, 10 ** 6), 1) == 10 ** 6
+    assert k.dense_sum_cells((4, 5), 0) == 5
+    for shape, axis in (((6, 5, 4), 0), ((6, 5, 4), 1), ((6, 5, 4), 2), ((7, 1, 1), 0)):
+        assert _plan.axis_sum_plan(shape, axis) == _plan.axis_sum_plan(list(shape), axis)
+        assert _plan.axis_sum_plan(shape, axis) is _plan.axis_sum_plan(shape, axis)      # cached
+    assert _plan.axis_sum_plan((6, 5, 4), 2) == ("last", 4)
+    assert _plan.axis_sum_plan((7, 1, 1), 0) == ("last", 7)
+    ndim, ins, outs, keep = k._stride_args((20, 4, 1), (4, 0, 1))
+    assert ndim == 3 and list(keep[0]) == [20, 4, 1] and list(keep[1]) == [4, 0, 1]
+    assert k._stride_args((20, 4, 1), (4, 0, 1))[1] is ins                       # cached: the arrays stay alive
