@@ -429,7 +429,11 @@ setop_kernel(const SetopParams p) {
         }
         fence_mbar_init();
     }
-    __syncthreads();                                                   // barriers initialised (all warps)
+    // unions: every warp needs the initialised barriers before the helper (another warp than thread 0's)
+    // may use them.  Intersections: thread 0 sits in the staging warp itself, so a warp-level sync is
+    // enough there and the others learn about the barrier through (A).
+    if constexpr (KIND == KIND_UNION) __syncthreads();
+    else __syncwarp();
 
     if (warp == kHelper) {
         // ---- stage the tile: descriptor -> TMA bulk copies, ragged edges, sentinels -------------
@@ -534,11 +538,12 @@ setop_kernel(const SetopParams p) {
         // merge_reorder_kernel moves the chunks into tile order.
         if (tid == 0) {
             int64_t slot = tile * kFixedSlots;
-            if (tile_total > kFixedSlots)
+            if (tile_total > kFixedSlots) {
                 slot = p.ntiles * kFixedSlots + (int64_t)atomicAdd(p.slot_counter, (unsigned long long)tile_total);
+                *base_s = slot;
+            }
             p.tile_slot[tile] = slot;
             p.tile_cnt[tile] = tile_total;
-            *base_s = slot;
         }
     } else if (tid == 0) {
         // publish the count for the successors, and hand it to the helper warp (which has been looking
@@ -554,8 +559,11 @@ setop_kernel(const SetopParams p) {
     VO* ev = sval;
     int64_t *epa = spa, *epb = spb_;
     if constexpr (KIND == KIND_INTERSECT) {
-        __syncthreads();                                               // slot of this tile visible
-        const int64_t slot = *base_s;
+        int64_t slot = tile * kFixedSlots;                             // the tile's own slots: no round trip, no barrier
+        if (tile_total > kFixedSlots) {                                // (uniform) overflow: thread 0 reserved room
+            __syncthreads();
+            slot = *base_s;
+        }
         ek = p.tmp_idx + slot;
         ev = reinterpret_cast<VO*>(p.tmp_val) + slot;
         epa = p.tmp_apos + slot;
