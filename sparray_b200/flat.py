@@ -16,6 +16,9 @@ Deliberate divergences from the reference:
     queries and numpy semantics for repeated ones;
   * broadcasting between sparse operands stays sparse (index-expansion kernel + sort)
     instead of densifying (flat.py:470-472);
+  * results whose size depends on the data are lazily counted: the element count is read back from
+    the device when ``indices`` / ``data`` / ``nnz`` are first looked at, not when the op returns
+    (invisible to callers; it keeps chains such as ``(a * b).sum(axis=2)`` free of host waits);
   * branches whose RESULT is dense by nature in the reference and that involve no dense
     operand (sparse + nonzero scalar, sparse / sparse, sparse ** 0, ...) are out of the
     hot-path scope and raise NotImplementedError; fancy assignment raises like the reference.
