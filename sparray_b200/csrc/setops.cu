@@ -512,6 +512,18 @@ setop_kernel(const SetopParams p) {
         merge_walk<WideKeys, KIND, kVT>(A, B, ai0, bi0, steps, prev_eq, m_ta, m_eq, m_emit);
     }
 
+    // intersections: the two values of this thread's FIRST match are requested now, so that the gather
+    // latency overlaps the scan and its barrier (a thread rarely has a second match)
+    [[maybe_unused]] V pre_x = V(0), pre_y = V(0);
+    if constexpr (KIND == KIND_INTERSECT && HAS_VAL) {
+        if (m_emit) {
+            const int k = __ffs(m_emit) - 1;
+            const int na_before = __popc(m_ta & ((1u << k) - 1u));
+            pre_x = __ldg(reinterpret_cast<const V*>(p.a_val) + g.a0 + ai0 + na_before);
+            pre_y = __ldg(reinterpret_cast<const V*>(p.b_val) + g.b0 + bi0 + k - na_before);
+        }
+    }
+
     // ---- block exclusive scan of the output counts -------------------------------------------
     const int cnt = __popc(m_emit);
     int incl = cnt;
@@ -573,6 +585,7 @@ setop_kernel(const SetopParams p) {
         // matches are rare: visit only the set bits (the item's position in A / B follows from the
         // took-A mask, no walk needed)
         unsigned m = m_emit;
+        bool first = true;
         while (m) {
             const int k = __ffs(m) - 1;
             m &= m - 1;
@@ -580,8 +593,10 @@ setop_kernel(const SetopParams p) {
             const int ai = ai0 + na_before, bi = bi0 + k - na_before;
             ek[off] = As64[ai];
             if constexpr (HAS_VAL) {
-                const V x = __ldg(reinterpret_cast<const V*>(p.a_val) + g.a0 + ai);   // only matched values are read
-                V y = __ldg(reinterpret_cast<const V*>(p.b_val) + g.b0 + bi);
+                // only matched values are read (the first pair was requested before the scan)
+                const V x = first ? pre_x : __ldg(reinterpret_cast<const V*>(p.a_val) + g.a0 + ai);
+                V y = first ? pre_y : __ldg(reinterpret_cast<const V*>(p.b_val) + g.b0 + bi);
+                first = false;
                 if (p.negate_b) y = (V)(-y);
                 ev[off] = value_op<V, VO>(p.op, x, y);
             }
