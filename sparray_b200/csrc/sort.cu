@@ -411,8 +411,20 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
         n = m < n ? m : n;
     }
     const int lane = threadIdx.x & 31;
-    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    if (n <= nthreads) {
+        // few elements (typically a lazily counted product whose real count is far below its upper bound):
+        // one element per thread, no aggregation -- the shortest critical path
+        if (gtid < n) {
+            const int64_t key = apply_rekey(__ldcs(idx + gtid), rk);
+            atomicAdd(acc + key, (double)__ldcs(val + gtid));
+            touched[key] = 1;
+        }
+        return;
+    }
+    const int64_t warp_global = gtid >> 5;
+    const int64_t nwarps = nthreads >> 5;
     const int64_t chunk = 32 * kAccUnroll;
     for (int64_t base = warp_global * chunk; base < n; base += nwarps * chunk) {
         int64_t key[kAccUnroll];
