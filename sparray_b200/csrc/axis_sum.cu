@@ -1,0 +1,342 @@
+// sparray_b200/csrc/axis_sum.cu -- sum(axis) into dense float64 accumulators (no sort).
+//
+// Replaces the unravel / re-ravel + np.unique + np.bincount of FlatSparray.sum (flat.py:617-625)
+// whenever the reduced array is small enough to hold densely.
+#include "rekey.cuh"
+
+// ---- axis sums into a dense accumulator (no sort) ---------------------------------------------------
+// When the reduced array prod(new_shape) is small enough to hold densely, sum(axis != last)
+// (flat.py:617-625) does not need the re-key + radix sort at all: every stored element adds its
+// value into acc[new_key] with a float64 atomic (the accumulator is L2-resident for the BASELINE
+// configs), marks the cell as touched (explicit zeros must survive, so "sum == 0" cannot be the
+// test), and one compaction pass over the cells emits the touched ones in key order.
+namespace spb {
+
+// A warp reads 32 consecutive elements (coalesced), re-keys them, combines runs of equal new keys with a
+// segmented shuffle scan (when the reduced axis is the last one the elements of an output cell are
+// contiguous; otherwise runs are rare and the scan is a few wasted instructions) and the last lane of
+// each run adds the run's sum into its cell with one float64 atomic.
+constexpr int kAccUnroll = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
+                                                              int64_t n, const int64_t* __restrict__ n_dev,
+                                                              const Rekey rk, double* __restrict__ acc,
+                                                              uint8_t* __restrict__ touched) {
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();   // operands (and n_dev) may come from the previous launch
+    if (n_dev) {                       // the producer's count never left the device; n is its upper bound
+        const int64_t m = *n_dev;
+        n = m < n ? m : n;
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    if (n <= nthreads) {
+        // few elements (typically a lazily counted product whose real count is far below its upper bound):
+        // one element per thread, no aggregation -- the shortest critical path
+        if (gtid < n) {
+            const int64_t key = apply_rekey(__ldcs(idx + gtid), rk);
+            atomicAdd(acc + key, (double)__ldcs(val + gtid));
+            touched[key] = 1;
+        }
+        return;
+    }
+    const int64_t warp_global = gtid >> 5;
+    const int64_t nwarps = nthreads >> 5;
+    const int64_t chunk = 32 * kAccUnroll;
+    for (int64_t base = warp_global * chunk; base < n; base += nwarps * chunk) {
+        int64_t key[kAccUnroll];
+        double v[kAccUnroll];
+#pragma unroll
+        for (int u = 0; u < kAccUnroll; ++u) {
+            const int64_t i = base + u * 32 + lane;
+            key[u] = i < n ? __ldcs(idx + i) : -1;
+            v[u] = i < n ? (double)__ldcs(val + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kAccUnroll; ++u)
+            if (key[u] >= 0) key[u] = apply_rekey(key[u], rk);
+#pragma unroll
+        for (int u = 0; u < kAccUnroll; ++u) {
+            // runs = maximal stretches of ADJACENT lanes with the same key (equal keys further apart are
+            // separate runs and simply cost one more atomic)
+            const int64_t kprev = __shfl_up_sync(0xffffffffu, key[u], 1);
+            const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || kprev != key[u]);
+            const int start = 31 - __clz(heads & ((2u << lane) - 1u));       // first lane of my run
+            double s = v[u];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane - o >= start) s += up;
+            }
+            const bool last = lane == 31 || ((heads >> (lane + 1)) & 1u);
+            if (key[u] >= 0 && last) {
+                atomicAdd(acc + key[u], s);
+                touched[key[u]] = 1;               // a flag per cell: explicit zeros survive
+            }
+        }
+    }
+}
+
+// Variant for LONG runs (reduced axis innermost and many elements per output cell): a lane owns kAccItems
+// CONSECUTIVE elements (one or two sectors), a warp 128.  The lane re-keys its
+// elements and adds up those that fall into the same cell as its first one as long as they are adjacent
+// (when the reduced axis is the last one the elements of a cell are contiguous, so a lane usually holds
+// ONE run); a lane holding a single run hands (cell, sum) to one segmented shuffle scan per 128 elements,
+// whose run ends issue one float64 atomic each; a lane holding several runs adds its pieces atomically
+// on its own.
+constexpr int kAccItems = 4;
+
+__device__ __forceinline__ double warp_run_sum(int64_t cell, double s, int lane, bool& last) {
+    const int64_t cprev = __shfl_up_sync(0xffffffffu, cell, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || cprev != cell || cell < 0);
+    const int start = 31 - __clz(heads & ((2u << lane) - 1u));       // first lane of my run
+    if (heads != 0xffffffffu) {                                       // some run is longer than one lane
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane - o >= start) s += up;
+        }
+    }
+    last = lane == 31 || ((heads >> (lane + 1)) & 1u);
+    return s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) axis_accumulate_runs_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
+                                                              int64_t n, const int64_t* __restrict__ n_dev,
+                                                              const Rekey rk, double* __restrict__ acc,
+                                                              uint8_t* __restrict__ touched) {
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();   // operands (and n_dev) may come from the previous launch
+    if (n_dev) {                       // the producer's count never left the device; n is its upper bound
+        const int64_t m = *n_dev;
+        n = m < n ? m : n;
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t chunk = 32 * kAccItems;
+    for (int64_t base = warp_global * chunk; base < n; base += nwarps * chunk) {
+        const int64_t i0 = base + (int64_t)lane * kAccItems;
+        int64_t key[kAccItems];
+        double v[kAccItems];
+#pragma unroll
+        for (int j = 0; j < kAccItems; ++j) {
+            key[j] = i0 + j < n ? __ldcs(idx + i0 + j) : -1;
+            v[j] = i0 + j < n ? (double)__ldcs(val + i0 + j) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < kAccItems; ++j)
+            if (key[j] >= 0) key[j] = apply_rekey(key[j], rk);
+        // my runs of adjacent equal cells: all but a single whole-lane run go in atomically right here
+        const bool single = key[0] >= 0 && key[0] == key[1] && key[1] == key[2] && key[2] == key[3];
+        int64_t cell = -2 - lane;      // negative and distinct: takes no part in the warp's runs
+        double s = 0.0;
+        if (single) {
+            cell = key[0];
+            s = (v[0] + v[1]) + (v[2] + v[3]);
+        } else {
+            int64_t run = -1;
+            double rs = 0.0;
+#pragma unroll
+            for (int j = 0; j < kAccItems; ++j) {
+                if (key[j] >= 0) {
+                    if (key[j] != run) {
+                        if (run >= 0) {
+                            atomicAdd(acc + run, rs);
+                            touched[run] = 1;
+                        }
+                        run = key[j];
+                        rs = v[j];
+                    } else {
+                        rs += v[j];
+                    }
+                }
+            }
+            if (run >= 0) {
+                atomicAdd(acc + run, rs);
+                touched[run] = 1;       // a flag per cell: explicit zeros survive
+            }
+        }
+        bool last;
+        s = warp_run_sum(cell, s, lane, last);
+        if (cell >= 0 && last) {
+            atomicAdd(acc + cell, s);
+            touched[cell] = 1;
+        }
+    }
+}
+
+// Emits the touched cells in key order and puts every cell it emitted back to zero, so the
+// accumulator slab is all-zero again when the call is over (no memset per call).  One thread owns
+// 64 cells (four 16-byte loads of flag bytes); a tile of 256 threads covers 16 K cells, which keeps
+// the look-back chain short.
+__global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict__ acc, uint8_t* __restrict__ touched,
+                                                             int64_t cells, int64_t key_base, int64_t* __restrict__ out_idx,
+                                                             double* __restrict__ out_val, int64_t* out_count,
+                                                             uint64_t* state, uint32_t epoch) {
+    const int64_t tile = blockIdx.x;
+    const int64_t first = (tile * 256 + threadIdx.x) * 64;
+    cudaGridDependencySynchronize();   // accumulators come from the previous launch
+    unsigned long long bits = 0;
+    if (first < cells) {               // the flag array is padded to a multiple of 64 (the padding stays zero)
+        uint4* const flags = reinterpret_cast<uint4*>(touched + first);
+        uint4 raw[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) raw[q] = flags[q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned w[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                bits |= (unsigned long long)((w[k >> 2] >> (8 * (k & 3))) & 1u) << (16 * q + k);
+            if (raw[q].x | raw[q].y | raw[q].z | raw[q].w) flags[q] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    const int cnt = __popcll(bits);
+    const int64_t off = compact_offset_256<true>(cnt, state, epoch, tile, tile == gridDim.x - 1, out_count);
+    // Warp-cooperative emission: the warp's outputs are one contiguous run, written 32 at a time (coalesced
+    // whether the cells are nearly all touched or nearly all empty).  Output r of the warp belongs to the
+    // first lane whose inclusive count exceeds r, and is that lane's (r - exclusive count)-th set bit.
+    const int lane = threadIdx.x & 31;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    const int64_t warp_off = __shfl_sync(0xffffffffu, off, 0);
+    const int64_t warp_first = first - (int64_t)lane * 64;
+    for (int c = 0; c < warp_total; c += 32) {
+        const int r = c + lane;
+        int owner = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int probe = __shfl_sync(0xffffffffu, incl, owner + step - 1);
+            if (probe <= r) owner += step;
+        }
+        owner = owner > 31 ? 31 : owner;
+        const int owner_excl = __shfl_sync(0xffffffffu, incl - cnt, owner);
+        const unsigned lo_bits = __shfl_sync(0xffffffffu, (unsigned)bits, owner);
+        const unsigned hi_bits = __shfl_sync(0xffffffffu, (unsigned)(bits >> 32), owner);
+        if (r < warp_total) {
+            const int j = r - owner_excl, nlo = __popc(lo_bits);
+            const int k = j < nlo ? (int)__fns(lo_bits, 0, j + 1) : 32 + (int)__fns(hi_bits, 0, j - nlo + 1);
+            const int64_t cell = warp_first + (int64_t)owner * 64 + k;
+            out_idx[warp_off + r] = key_base + cell;
+            out_val[warp_off + r] = acc[cell];
+            acc[cell] = 0.0;
+        }
+    }
+}
+
+}  // namespace spb
+
+namespace spb {
+
+static int launch_accumulate(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev,
+                             const Rekey& rk, int64_t cells, double* acc, uint8_t* touched, cudaStream_t stream) {
+    int64_t blocks = ceil_div(n, 256 * kAccUnroll);
+    if (blocks > (int64_t)device_sm_count() * 16) blocks = (int64_t)device_sm_count() * 16;
+    // long contiguous runs (innermost axis reduced, >= 8 elements per output cell on average): the variant
+    // that pre-reduces inside a lane and scans once per 128 elements
+    const bool long_runs = rk.ndim >= 1 && rk.out_mul[rk.ndim - 1] == 0 && n >= 8 * cells;
+#define SPB_ACC(T)                                                                                            \
+    if (long_runs) {                                                                                          \
+        SPB_CUDA_TRY(launch_pdl(axis_accumulate_runs_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, \
+                                idx, (const T*)val, n, n_dev, rk, acc, touched));                             \
+    } else {                                                                                                  \
+        SPB_CUDA_TRY(launch_pdl(axis_accumulate_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, idx, \
+                                (const T*)val, n, n_dev, rk, acc, touched));                                  \
+    }                                                                                                         \
+    break
+    switch (dtype) {
+        case SPB_F32: SPB_ACC(float);
+        case SPB_F64: SPB_ACC(double);
+        case SPB_I32: SPB_ACC(int32_t);
+        case SPB_I64: SPB_ACC(int64_t);
+        case SPB_U8: case SPB_BOOL: SPB_ACC(uint8_t);
+        case SPB_I8: SPB_ACC(int8_t);
+        case SPB_I16: SPB_ACC(int16_t);
+        default: return SPB_ERR_UNSUPPORTED;
+    }
+#undef SPB_ACC
+    SPB_LAUNCHED(1);
+    return (int)cudaGetLastError();
+}
+
+// cells of [0, cells) relative to acc / touched (touched readable up to the next multiple of 64)
+static int launch_select(double* acc, uint8_t* touched, int64_t cells, int64_t key_base, int64_t* out_idx,
+                         double* out_sums, int64_t* out_count, spb_workspace* ws, cudaStream_t stream) {
+    const int64_t ntiles = ceil_div(cells, 256 * 64);
+    if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
+    int rc = workspace_reserve(ws, (size_t)ntiles * 8, stream);
+    if (rc) return rc;
+    uint32_t epoch;
+    rc = workspace_next_epoch(ws, stream, &epoch);
+    if (rc) return rc;
+    SPB_CUDA_TRY(launch_pdl(select_touched_kernel, dim3((unsigned)ntiles), dim3(256), 0, stream, acc, touched, cells,
+                            key_base, out_idx, out_sums, out_count, ws_state(ws), epoch));
+    SPB_LAUNCHED(1);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace spb
+
+extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev, int ndim,
+                                  const int64_t* in_strides, const int64_t* out_strides, int64_t cells,
+                                  int64_t* out_idx, double* out_sums, int64_t* out_count,
+                                  spb_workspace* ws, spb_stream_t stream) {
+    using namespace spb;
+    if (n < 0 || cells < 0 || !out_count) return SPB_ERR_BAD_ARG;
+    Rekey rk{};
+    if (ndim < 1) return SPB_ERR_BAD_ARG;
+    int rc = make_rekey(rk, ndim, in_strides, out_strides);
+    if (rc) return rc;
+    if (n == 0 || cells == 0) return (int)cudaMemsetAsync(out_count, 0, 8, stream);
+    if (!idx || !val || !out_idx || !out_sums || !ws) return SPB_ERR_BAD_ARG;
+    // accumulators (cells doubles) then one flag byte per cell (padded to 64) in the workspace's self-cleaning slab
+    const size_t acc_bytes = ((size_t)cells * sizeof(double) + 255) & ~(size_t)255;
+    const int64_t nflags = ceil_div(cells, 64) * 64;
+    rc = workspace_reserve_accum(ws, acc_bytes + (size_t)nflags, stream);
+    if (rc) return rc;
+    double* const acc = reinterpret_cast<double*>(ws->accum);
+    uint8_t* const touched = reinterpret_cast<uint8_t*>(ws->accum) + acc_bytes;
+    rc = launch_accumulate(dtype, idx, val, n, n_dev, rk, cells, acc, touched, stream);
+    if (rc) return rc;
+    return launch_select(acc, touched, cells, 0, out_idx, out_sums, out_count, ws, stream);
+}
+
+// The two halves on caller-owned buffers, for the sharded axis sum (all-reduce of the accumulators
+// between them): acc = cells doubles, touched = cells flag bytes padded to a multiple of 64, both
+// zeroed by the caller, touched 16-byte aligned.
+extern "C" int spb_axis_accumulate(int dtype, const int64_t* idx, const void* val, int64_t n, int ndim,
+                                   const int64_t* in_strides, const int64_t* out_strides, int64_t cells, double* acc,
+                                   uint8_t* touched, spb_stream_t stream) {
+    using namespace spb;
+    if (n < 0 || cells < 0) return SPB_ERR_BAD_ARG;
+    Rekey rk{};
+    if (ndim < 1) return SPB_ERR_BAD_ARG;
+    const int rc = make_rekey(rk, ndim, in_strides, out_strides);
+    if (rc) return rc;
+    if (n == 0 || cells == 0) return SPB_OK;
+    if (!idx || !val || !acc || !touched) return SPB_ERR_BAD_ARG;
+    return launch_accumulate(dtype, idx, val, n, nullptr, rk, cells, acc, touched, stream);
+}
+
+// Emit the touched cells of [cell_lo, cell_hi) in key order (keys are absolute cell numbers).
+// cell_lo must be a multiple of 64 (flag words are read 16 bytes at a time); the cells that are
+// emitted are zeroed.  out_idx / out_sums: cell_hi - cell_lo slots.
+extern "C" int spb_emit_touched(double* acc, uint8_t* touched, int64_t cell_lo, int64_t cell_hi, int64_t* out_idx,
+                                double* out_sums, int64_t* out_count, spb_workspace* ws, spb_stream_t stream) {
+    using namespace spb;
+    if (cell_lo < 0 || cell_hi < cell_lo || (cell_lo & 63) != 0 || !out_count) return SPB_ERR_BAD_ARG;
+    if (cell_hi == cell_lo) return (int)cudaMemsetAsync(out_count, 0, 8, stream);
+    if (!acc || !touched || !out_idx || !out_sums || !ws) return SPB_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(touched) & 15) != 0) return SPB_ERR_BAD_ARG;
+    return launch_select(acc + cell_lo, touched + cell_lo, cell_hi - cell_lo, cell_lo, out_idx, out_sums, out_count, ws,
+                         stream);
+}

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/sparray_b200.h"
 
 #ifndef __CUDA_ARCH_FEAT_SM100_ALL
@@ -36,8 +38,25 @@ struct spb_workspace {
 namespace spb {
 
 // number of kernels this library has launched (read back through spb_launch_count)
-extern unsigned long long g_launches;
-#define SPB_LAUNCHED(k) (::spb::g_launches += (k))
+extern std::atomic<unsigned long long> g_launches;
+#define SPB_LAUNCHED(k) (::spb::g_launches.fetch_add((k), std::memory_order_relaxed))
+
+// Function attributes (shared-memory carve-out, max dynamic shared memory) and occupancy answers are
+// per DEVICE: a process driving several GPUs must configure a kernel once on each.  One of these per
+// kernel instantiation; first_use() is true exactly once per device (and thread-safe).
+struct PerDevice {
+    std::atomic<uint64_t> seen{0};
+    int value[64] = {};
+    bool first_use(int dev) {
+        const uint64_t bit = 1ull << (dev & 63);
+        return (seen.fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
+    }
+};
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
 
 // Workspace layout: [0, kWsMiscBytes) plain scratch (reduction partials, histograms);
 // [kWsMiscBytes, ...) epoch-tagged look-back state words.  Only state words are ever

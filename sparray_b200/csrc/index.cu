@@ -204,7 +204,7 @@ int spb_outer_sum(const int64_t* offsets, int ndim, const int64_t* lens, int64_t
         stride *= lens[j];
     }
     int64_t blocks = ceil_div(n, 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (int64_t)device_sm_count() * 16) blocks = (int64_t)device_sm_count() * 16;
     outer_sum_kernel<<<(unsigned)blocks, 256, 0, stream>>>(offsets, o, out, n);
     SPB_LAUNCHED(1);
     return (int)cudaGetLastError();
@@ -308,7 +308,7 @@ extern "C" int spb_broadcast_expand(int dtype, const int64_t* idx, const void* v
     if (n_out == 0) return SPB_OK;
     if (!idx || !val || !out_idx || !out_val) return SPB_ERR_BAD_ARG;
     int64_t blocks = ceil_div(n_out, 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (int64_t)device_sm_count() * 16) blocks = (int64_t)device_sm_count() * 16;
 #define SPB_EXP(T)                                                                                              \
     broadcast_expand_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(idx, (const T*)val, n_out, e, out_idx,    \
                                                                      (T*)out_val);                              \

@@ -12,7 +12,7 @@ constexpr int kMapThreads = 256;
 
 inline unsigned grid_for(int64_t work_items, int per_block) {
     int64_t b = ceil_div(work_items, per_block);
-    const int64_t cap = 148 * 32;
+    const int64_t cap = (int64_t)device_sm_count() * 32;
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     return (unsigned)b;

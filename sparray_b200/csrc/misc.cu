@@ -6,7 +6,7 @@
 
 namespace spb {
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 constexpr int kMaxDims = 32;
 
@@ -57,7 +57,7 @@ const char* spb_error_string(int code) {
     }
 }
 
-unsigned long long spb_launch_count(void) { return g_launches; }
+unsigned long long spb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // host evaluation of the device-side exact division (same magic numbers): for the CPU tests
 uint64_t spb_debug_fastdiv(uint64_t n, uint64_t d) {
@@ -104,7 +104,7 @@ int spb_combine_ranges(const int64_t* ranges, const int64_t* shape, int ndim, in
         box *= p.len[ax];
     }
     int64_t blocks = ceil_div(result_size, 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (int64_t)device_sm_count() * 16) blocks = (int64_t)device_sm_count() * 16;
     combine_ranges_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, out, result_size);
     SPB_LAUNCHED(1);
     return (int)cudaGetLastError();

@@ -370,11 +370,10 @@ int launch_reduce(ReduceParams& p, spb_workspace* ws, cudaStream_t stream) {
     if (rc) return rc;
     p.entries = reinterpret_cast<Entry16*>(ws->state16);
     {
-        static bool configured = false;
-        if (!configured) {   // let the SM give this kernel all the shared memory it can use
+        static PerDevice configured;
+        if (configured.first_use(current_device())) {   // let the SM give this kernel all the shared memory it can use
             SPB_CUDA_TRY(cudaFuncSetAttribute(reduce_by_key_kernel<T>,
                                               cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            configured = true;
         }
     }
     reduce_by_key_kernel<T><<<(unsigned)ntiles, kRNT, 0, stream>>>(p);

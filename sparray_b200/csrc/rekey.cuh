@@ -1,0 +1,75 @@
+// sparray_b200/csrc/rekey.cuh -- index re-keying shared by the radix sort (sort.cu) and the dense
+// axis sums (axis_sum.cu): unravel a C-order flat index by the strides of (merged) axis groups of the
+// old shape, permute / drop groups, re-ravel with the strides of the new shape.  This is the
+// np.unravel_index + np.ravel_multi_index pair of FlatSparray.transpose (flat.py:109-111) and
+// FlatSparray.sum (flat.py:617-619) without the ndim int64 temporaries.
+#pragma once
+#include "common.cuh"
+
+namespace spb {
+
+constexpr int kMaxRekeyDims = 8;
+
+struct Rekey {
+    int ndim;                             // 0: identity
+    int pow2;                             // every in_div and every non-zero out_mul is a power of two
+    FastDiv in_div[kMaxRekeyDims];        // C-order stride of (merged) axis group ax in the old shape
+    int64_t out_mul[kMaxRekeyDims];       // its stride in the new shape; 0 = group dropped
+    int out_shift[kMaxRekeyDims];         // pow2: log2(out_mul), -1 = dropped
+};
+
+__device__ __forceinline__ int64_t apply_rekey(int64_t idx, const Rekey& r) {
+    if (r.ndim == 0) return idx;
+    uint64_t rem = (uint64_t)idx;
+    if (r.pow2) {
+        // power-of-two shapes (BASELINE configs 2, 3, 5): bit fields move, no multiplications
+        uint64_t acc = 0;
+#pragma unroll
+        for (int ax = 0; ax < kMaxRekeyDims - 1; ++ax) {
+            if (ax < r.ndim - 1) {
+                const uint64_t q = rem >> r.in_div[ax].shift;
+                rem &= r.in_div[ax].d - 1;
+                if (r.out_shift[ax] >= 0) acc |= q << r.out_shift[ax];
+            }
+        }
+        if (r.out_shift[r.ndim - 1] >= 0) acc |= rem << r.out_shift[r.ndim - 1];
+        return (int64_t)acc;
+    }
+    int64_t acc = 0;
+#pragma unroll
+    for (int ax = 0; ax < kMaxRekeyDims - 1; ++ax) {
+        if (ax < r.ndim - 1) {
+            const uint64_t q = fastdiv(rem, r.in_div[ax]);
+            rem -= q * r.in_div[ax].d;
+            acc += (int64_t)q * r.out_mul[ax];
+        }
+    }
+    return acc + (int64_t)rem * r.out_mul[r.ndim - 1];
+}
+
+// ndim == 0 gives the identity.  Returns SPB_OK or SPB_ERR_BAD_ARG.
+inline int make_rekey(Rekey& rk, int ndim, const int64_t* in_strides, const int64_t* out_strides) {
+    rk = Rekey{};
+    if (ndim < 0 || ndim > kMaxRekeyDims) return SPB_ERR_BAD_ARG;
+    if (ndim && (!in_strides || !out_strides)) return SPB_ERR_BAD_ARG;
+    rk.ndim = ndim;
+    rk.pow2 = 1;
+    for (int ax = 0; ax < ndim; ++ax) {
+        if (in_strides[ax] < 1 || out_strides[ax] < 0) return SPB_ERR_BAD_ARG;
+        rk.in_div[ax] = make_fastdiv((uint64_t)in_strides[ax]);
+        rk.out_mul[ax] = out_strides[ax];
+        rk.out_shift[ax] = -1;
+        const uint64_t m = (uint64_t)out_strides[ax];
+        if (rk.in_div[ax].magic != 0) rk.pow2 = 0;
+        if (m) {
+            if (m & (m - 1)) rk.pow2 = 0;
+            int s = 0;
+            while ((1ull << s) < m) ++s;
+            rk.out_shift[ax] = s;
+        }
+    }
+    if (ndim && in_strides[ndim - 1] != 1) return SPB_ERR_BAD_ARG;
+    return SPB_OK;
+}
+
+}  // namespace spb

@@ -110,6 +110,7 @@ struct SetopParams {
     unsigned long long* slot_counter;
     int64_t* tile_slot;      // [ntiles]
     int* tile_cnt;           // [ntiles]
+    int* group_cnt;          // [ceil(ntiles / kGroupTiles)] matches per group of tiles
     int64_t* tmp_idx;        // chunked outputs, min(na, nb) slots each
     void* tmp_val;
     int64_t* tmp_apos;
@@ -143,67 +144,87 @@ struct PartitionParams {
     int tile_items;          // merged items per tile
     int64_t ntiles;
     uint64_t* desc;          // [ntiles][kDescWords]
+    int* group_cnt;          // intersections: [ngroups] match counters to zero, else null
+    int64_t ngroups;
 };
 
 constexpr int64_t kGuessWindow = 8192;
 
-// Diagonals (tile boundaries) per CTA of the partition kernel: 16 half-warps search 16 consecutive
+// Diagonals (tile boundaries) per CTA of the partition kernel: 16 warps search 16 consecutive
 // diagonals, then 15 threads turn the 15 tiles between them into staging descriptors.
 constexpr int kPartTiles = 15;
+constexpr int kPartThreads = 512;
+constexpr int kGroupTiles = 64;          // intersections: tiles per group counter (see merge_reorder_kernel)
 
-// 16 lanes per diagonal (two diagonals per warp): a bracket probe + ~4 dependent rounds of 16 probe pairs
-__device__ __forceinline__ int64_t merge_split_halfwarp(const PartitionParams& p, int64_t w) {
-    const int lane16 = threadIdx.x & 15;
-    const unsigned gmask = 0xffffu << (threadIdx.x & 16);
+// One warp per diagonal.  Round 1 probes the bracket around the proportional guess (2 lanes) AND 30 points
+// inside it, so for operands of comparable density the search is three dependent rounds of probes (the
+// window shrinks 16384 -> ~550 -> ~18 -> found); anything else falls back to plain 32-ary rounds.
+__device__ __forceinline__ int64_t merge_split_warp(const PartitionParams& p, int64_t w) {
+    const int lane = threadIdx.x & 31;
     const int64_t total = p.na + p.nb;
     int64_t d = w * (int64_t)p.tile_items;
     if (d > total) d = total;
     int64_t lo = d > p.nb ? d - p.nb : 0;
     int64_t hi = d < p.na ? d : p.na;
-    // Bracket around the proportional guess first: two probes instead of two rounds of 16, and --
-    // more important -- the tile boundaries stop hammering the same few top-level keys (all ~10^4
-    // searches would otherwise hit the same 32 cache lines in their first round).
+    // predicate "the split lies above m": a[m] <= b[d-1-m]; true for m < split, false from the split on
     if (hi - lo > 4 * kGuessWindow) {
         const int64_t guess = (int64_t)(((unsigned __int128)(uint64_t)d * (uint64_t)p.na) / (uint64_t)total);
         int64_t lo2 = guess - kGuessWindow, hi2 = guess + kGuessWindow;
         if (lo2 < lo) lo2 = lo;
         if (hi2 > hi) hi2 = hi;
-        bool ok = true;
-        if (lane16 == 0 && lo2 > lo) ok = __ldg(p.a + lo2 - 1) <= __ldg(p.b + (d - lo2));        // answer >= lo2
-        if (lane16 == 1 && hi2 < hi) ok = !(__ldg(p.a + hi2) <= __ldg(p.b + (d - 1 - hi2)));     // answer <= hi2
-        const unsigned okb = (__ballot_sync(gmask, ok) >> (threadIdx.x & 16)) & 0xffffu;
-        if (okb == 0xffffu) {
-            lo = lo2;
-            hi = hi2;
+        // the tile boundaries stop hammering the same few top-level keys (all ~10^4 searches would
+        // otherwise hit the same 32 cache lines in their first round)
+        const int64_t span = hi2 - lo2;
+        int64_t m;
+        if (lane == 30) m = lo2 > lo ? lo2 - 1 : -1;                 // must be true: split >= lo2
+        else if (lane == 31) m = hi2 < hi ? hi2 : -2;                // must be false: split <= hi2
+        else m = lo2 + (span / 30) * lane + ((span % 30) * lane) / 30;
+        bool t;
+        if (m == -1) t = true;
+        else if (m == -2) t = false;
+        else if (m >= hi2 && lane < 30) t = false;                   // span == 0
+        else t = __ldg(p.a + m) <= __ldg(p.b + (d - 1 - m));
+        const unsigned bal = __ballot_sync(0xffffffffu, t);
+        if ((bal >> 30) == 1u) {                                     // bracket holds: lane 30 true, lane 31 false
+            const int c = __popc(bal & 0x3fffffffu);
+            const int64_t m_last_true = __shfl_sync(0xffffffffu, m, c > 0 ? c - 1 : 0);
+            const int64_t m_first_false = __shfl_sync(0xffffffffu, m, c < 30 ? c : 29);
+            lo = c > 0 ? m_last_true + 1 : lo2;
+            hi = c < 30 ? m_first_false : hi2;
         }
     }
     while (lo < hi) {
         const int64_t span = hi - lo;
-        const int64_t m = lo + ((span >> 4) * lane16) + (((span & 15) * lane16) >> 4);   // floor(span * lane / 16)
+        const int64_t m = lo + ((span >> 5) * lane) + (((span & 31) * lane) >> 5);   // floor(span * lane / 32)
         const bool take_a = __ldg(p.a + m) <= __ldg(p.b + (d - 1 - m));
-        const unsigned bal = (__ballot_sync(gmask, take_a) >> (threadIdx.x & 16)) & 0xffffu;
+        const unsigned bal = __ballot_sync(0xffffffffu, take_a);
         const int c = __popc(bal);
         if (c == 0) {
             hi = lo;
             break;
         }
-        const int src_base = threadIdx.x & 16;
-        const int64_t m_last_true = __shfl_sync(gmask, m, src_base + c - 1);
-        const int64_t m_first_false = __shfl_sync(gmask, m, src_base + (c < 16 ? c : 15));
+        const int64_t m_last_true = __shfl_sync(0xffffffffu, m, c - 1);
+        const int64_t m_first_false = __shfl_sync(0xffffffffu, m, c < 32 ? c : 31);
         lo = m_last_true + 1;
-        if (c < 16) hi = m_first_false;
+        if (c < 32) hi = m_first_false;
     }
     return lo;
 }
 
-__global__ void __launch_bounds__(256) merge_partition_kernel(const PartitionParams p) {
+__global__ void __launch_bounds__(kPartThreads) merge_partition_kernel(const PartitionParams p) {
     __shared__ int64_t s_split[16];
     cudaGridDependencySynchronize();               // the operands may come from the previous launch
+    // intersections: the per-group match counters start from zero (the merge kernel, which adds to them,
+    // waits for this whole grid)
+    if (p.group_cnt) {
+        const int64_t g = (int64_t)blockIdx.x * kPartThreads + threadIdx.x;
+        if (g < p.ngroups) p.group_cnt[g] = 0;
+    }
     {
-        int64_t w = (int64_t)blockIdx.x * kPartTiles + (threadIdx.x >> 4);   // diagonal index 0..ntiles
-        if (w > p.ntiles) w = p.ntiles;              // keep the half-warp converged on a valid diagonal
-        const int64_t sp = merge_split_halfwarp(p, w);
-        if ((threadIdx.x & 15) == 0) s_split[threadIdx.x >> 4] = sp;
+        int64_t w = (int64_t)blockIdx.x * kPartTiles + (threadIdx.x >> 5);   // diagonal index 0..ntiles
+        if (w > p.ntiles) w = p.ntiles;              // keep the warp converged on a valid diagonal
+        const int64_t sp = merge_split_warp(p, w);
+        if ((threadIdx.x & 31) == 0) s_split[threadIdx.x >> 5] = sp;
     }
     __syncthreads();
     const int64_t t = (int64_t)blockIdx.x * kPartTiles + threadIdx.x;
@@ -556,6 +577,7 @@ setop_kernel(const SetopParams p) {
             }
             p.tile_slot[tile] = slot;
             p.tile_cnt[tile] = tile_total;
+            if (tile_total) atomicAdd(p.group_cnt + tile / kGroupTiles, tile_total);
         }
     } else if (tid == 0) {
         // publish the count for the successors, and hand it to the helper warp (which has been looking
@@ -677,35 +699,26 @@ setop_kernel(const SetopParams p) {
 }
 
 // ---- intersections: put the reserved chunks in tile order -----------------------------------------
-// One warp per tile, 8 tiles per CTA.  Every CTA first sums the counts of all earlier tiles itself
-// (the count array is a few tens of KB and L2-resident), which is cheaper than a separate scan launch.
+// One warp per tile.  The output offset of a tile is the sum of the match counts of all earlier tiles:
+// the merge kernel also added every tile's count into one counter per group of 64 tiles, so a warp sums
+// (at most ntiles/64) group counters and (at most 63) tile counts -- a single round of independent L2
+// loads, no scan launch, no look-back.
 template <int VBYTES>
 __global__ void __launch_bounds__(256) merge_reorder_kernel(const SetopParams p) {
-    __shared__ int64_t s_part[8];
-    __shared__ int s_cnt[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t first_tile = (int64_t)blockIdx.x * 8;
+    const int64_t t = (int64_t)blockIdx.x * 8 + warp;
     cudaTriggerProgrammaticLaunchCompletion();
     cudaGridDependencySynchronize();               // chunks and counts come from the previous launch
     if (blockIdx.x == 0 && tid == 0) *p.slot_counter = 0;   // every reservation is done: ready for the next call
+    if (t >= p.ntiles) return;
+    const int64_t g = t / kGroupTiles;
     int64_t acc = 0;
-    for (int64_t t = tid; t < first_tile; t += 256) acc += __ldg(p.tile_cnt + t);
+    for (int64_t j = lane; j < g; j += 32) acc += __ldg(p.group_cnt + j);
+    for (int64_t j = g * kGroupTiles + lane; j < t; j += 32) acc += __ldg(p.tile_cnt + j);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    const int64_t t = first_tile + warp;
-    const int n = t < p.ntiles ? p.tile_cnt[t] : 0;
-    if (lane == 0) {
-        s_part[warp] = acc;
-        s_cnt[warp] = n;
-    }
-    __syncthreads();
-    int64_t d = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        d += s_part[w];
-        if (w < warp) d += s_cnt[w];
-    }
-    if (t >= p.ntiles) return;
+    const int64_t d = acc;
+    const int n = p.tile_cnt[t];
     if (t == p.ntiles - 1 && lane == 0) *p.out_count = d + n;
     const int64_t src = p.tile_slot[t];
     for (int i = lane; i < n; i += 32) {
@@ -738,7 +751,9 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     size_t off_slot = off_splits + (size_t)(ntiles + 1) * 8;
     size_t off_dst = off_slot + (size_t)ntiles * 8;
     size_t off_cnt = off_dst + (size_t)ntiles * 8;
-    size_t off_counter = (off_cnt + (size_t)ntiles * 4 + 15) & ~(size_t)15;
+    const int64_t ngroups = ceil_div(ntiles, kGroupTiles);
+    size_t off_group = (off_cnt + (size_t)ntiles * 4 + 15) & ~(size_t)15;
+    size_t off_counter = (off_group + (size_t)ngroups * 4 + 15) & ~(size_t)15;
     size_t off_tidx = off_counter + 16;
     size_t off_tval = off_tidx + cap * 8;
     size_t off_tapos = off_tval + cap * 8;
@@ -752,12 +767,10 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     p.ntiles = ntiles;
     p.desc = reinterpret_cast<uint64_t*>(ws->payload);
     auto kern = setop_kernel<V, VO, KIND, HAS_VAL, SEAM>;
-    static int ctas_per_sm = 0;
-    if (!ctas_per_sm) {
+    static PerDevice configured;       // function attributes are per device
+    if (configured.first_use(current_device())) {
         SPB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         SPB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        SPB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, C::kThreads, smem));
-        if (ctas_per_sm < 1) return SPB_ERR_UNSUPPORTED;
     }
     PartitionParams pp{};
     pp.a = p.a; pp.b = p.b; pp.na = p.na; pp.nb = p.nb;
@@ -768,13 +781,16 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     if (KIND == KIND_INTERSECT) {
         p.tile_slot = reinterpret_cast<int64_t*>(pay + off_slot);
         p.tile_cnt = reinterpret_cast<int*>(pay + off_cnt);
+        p.group_cnt = reinterpret_cast<int*>(pay + off_group);
+        pp.group_cnt = p.group_cnt;
+        pp.ngroups = ngroups;
         p.slot_counter = ws_counters(ws);          // zero between calls: the reorder pass resets it
         p.tmp_idx = reinterpret_cast<int64_t*>(pay + off_tidx);
         p.tmp_val = pay + off_tval;
         p.tmp_apos = reinterpret_cast<int64_t*>(pay + off_tapos);
         p.tmp_bpos = reinterpret_cast<int64_t*>(pay + off_tbpos);
     }
-    SPB_CUDA_TRY(launch_pdl(merge_partition_kernel, dim3((unsigned)ceil_div(ntiles, kPartTiles)), dim3(256), 0, stream, pp));
+    SPB_CUDA_TRY(launch_pdl(merge_partition_kernel, dim3((unsigned)ceil_div(ntiles, kPartTiles)), dim3(kPartThreads), 0, stream, pp));
     SPB_LAUNCHED(1);
     SPB_CUDA_TRY(launch_pdl(kern, dim3((unsigned)ntiles), dim3(C::kThreads), (size_t)smem, stream, p));
     SPB_LAUNCHED(1);

@@ -18,7 +18,9 @@ int workspace_reserve(spb_workspace* ws, size_t state_bytes, cudaStream_t stream
     SPB_CUDA_TRY(cudaMalloc(&ws->dev, want + kWsCounterBytes));
     SPB_CUDA_TRY(cudaMemsetAsync(ws->dev, 0, want + kWsCounterBytes, stream));
     ws->bytes = want;
-    ws->epoch = 0;
+    // The epoch counter keeps running: the fresh buffer is all zero (= "invalid" in every epoch), while
+    // the 16-byte entries of state16 are NOT reallocated here and still hold words tagged with earlier
+    // epochs -- replaying 1, 2, 3... would make them look live again.
     return SPB_OK;
 }
 
@@ -82,14 +84,15 @@ int workspace_next_epoch(spb_workspace* ws, cudaStream_t stream, uint32_t* epoch
 }
 
 int device_sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+    static std::atomic<int> sms[64];
+    const int dev = current_device() & 63;
+    int v = sms[dev].load(std::memory_order_relaxed);
+    if (!v) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v <= 0) v = 148;
+        sms[dev].store(v, std::memory_order_relaxed);
     }
-    return sms;
+    return v;
 }
 
 }  // namespace spb
