@@ -27,6 +27,9 @@ class SparrayB200Error(RuntimeError):
 
 
 def _load():
+    override = os.environ.get("SPB_LIB_PATH")       # kernel A/B experiments (profiles/build_variant.py): a prebuilt variant
+    if override:
+        return ctypes.CDLL(override)
     if _build.needs_build():
         # normally built in-tree by __graft_entry__.build(); rebuild here when the sources changed
         try:

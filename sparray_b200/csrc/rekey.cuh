@@ -16,33 +16,48 @@ struct Rekey {
     FastDiv in_div[kMaxRekeyDims];        // C-order stride of (merged) axis group ax in the old shape
     int64_t out_mul[kMaxRekeyDims];       // its stride in the new shape; 0 = group dropped
     int out_shift[kMaxRekeyDims];         // pow2: log2(out_mul), -1 = dropped
+    uint64_t gmask[kMaxRekeyDims];        // pow2: (size of the group) - 1; all ones for the outermost group
 };
 
-__device__ __forceinline__ int64_t apply_rekey(int64_t idx, const Rekey& r) {
-    if (r.ndim == 0) return idx;
-    uint64_t rem = (uint64_t)idx;
+// NDIM known at compile time: straight-line code, no per-axis predicates
+template <int NDIM>
+__device__ __forceinline__ int64_t apply_rekey_n(uint64_t idx, const Rekey& r) {
     if (r.pow2) {
-        // power-of-two shapes (BASELINE configs 2, 3, 5): bit fields move, no multiplications
+        // power-of-two shapes (BASELINE configs 2, 3, 5): every group is a bit field that moves
         uint64_t acc = 0;
 #pragma unroll
-        for (int ax = 0; ax < kMaxRekeyDims - 1; ++ax) {
-            if (ax < r.ndim - 1) {
-                const uint64_t q = rem >> r.in_div[ax].shift;
-                rem &= r.in_div[ax].d - 1;
-                if (r.out_shift[ax] >= 0) acc |= q << r.out_shift[ax];
-            }
+        for (int ax = 0; ax < NDIM; ++ax) {
+            const uint64_t q = (idx >> r.in_div[ax].shift) & r.gmask[ax];
+            if (r.out_shift[ax] >= 0) acc |= q << r.out_shift[ax];
         }
-        if (r.out_shift[r.ndim - 1] >= 0) acc |= rem << r.out_shift[r.ndim - 1];
         return (int64_t)acc;
     }
+    uint64_t rem = idx;
     int64_t acc = 0;
 #pragma unroll
-    for (int ax = 0; ax < kMaxRekeyDims - 1; ++ax) {
-        if (ax < r.ndim - 1) {
-            const uint64_t q = fastdiv(rem, r.in_div[ax]);
-            rem -= q * r.in_div[ax].d;
-            acc += (int64_t)q * r.out_mul[ax];
-        }
+    for (int ax = 0; ax < NDIM - 1; ++ax) {
+        const uint64_t q = fastdiv(rem, r.in_div[ax]);
+        rem -= q * r.in_div[ax].d;
+        acc += (int64_t)q * r.out_mul[ax];
+    }
+    return acc + (int64_t)rem * r.out_mul[NDIM - 1];
+}
+
+__device__ __forceinline__ int64_t apply_rekey(int64_t idx, const Rekey& r) {
+    switch (r.ndim) {
+        case 0: return idx;
+        case 1: return apply_rekey_n<1>((uint64_t)idx, r);
+        case 2: return apply_rekey_n<2>((uint64_t)idx, r);
+        case 3: return apply_rekey_n<3>((uint64_t)idx, r);
+        case 4: return apply_rekey_n<4>((uint64_t)idx, r);
+        default: break;
+    }
+    uint64_t rem = (uint64_t)idx;
+    int64_t acc = 0;
+    for (int ax = 0; ax < r.ndim - 1; ++ax) {
+        const uint64_t q = fastdiv(rem, r.in_div[ax]);
+        rem -= q * r.in_div[ax].d;
+        acc += (int64_t)q * r.out_mul[ax];
     }
     return acc + (int64_t)rem * r.out_mul[r.ndim - 1];
 }
@@ -59,6 +74,7 @@ inline int make_rekey(Rekey& rk, int ndim, const int64_t* in_strides, const int6
         rk.in_div[ax] = make_fastdiv((uint64_t)in_strides[ax]);
         rk.out_mul[ax] = out_strides[ax];
         rk.out_shift[ax] = -1;
+        rk.gmask[ax] = ax == 0 ? ~0ull : (uint64_t)(in_strides[ax - 1] / in_strides[ax]) - 1;
         const uint64_t m = (uint64_t)out_strides[ax];
         if (rk.in_div[ax].magic != 0) rk.pow2 = 0;
         if (m) {

@@ -131,6 +131,23 @@ __global__ void __launch_bounds__(256) radix_scan_kernel(uint64_t* hist) {
     h[t] = wofs + incl - mine;
 }
 
+// Optional phase timers (-DSPB_SORT_TIMING, profiles/time_sort_phases.py): thread 0 of every CTA stamps the
+// global nanosecond timer at phase boundaries into a buffer registered with spb_debug_sort_timing().
+#ifdef SPB_SORT_TIMING
+__device__ unsigned long long* g_sort_timing = nullptr;     // [ntiles][16]
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define SPB_STAMP(slot)                                                                        \
+    do {                                                                                       \
+        if (threadIdx.x == 0 && g_sort_timing) g_sort_timing[blockIdx.x * 16 + (slot)] = gtimer(); \
+    } while (0)
+#else
+#define SPB_STAMP(slot) do { } while (0)
+#endif
+
 // ---- one digit pass -----------------------------------------------------------------------------
 struct PassParams {
     const void* keys_in;        // FIRST: int64 old keys; else packed keys (u32 / u64)
@@ -160,24 +177,39 @@ template <> struct ValType<2> { using type = uint16_t; };
 template <> struct ValType<4> { using type = uint32_t; };
 template <> struct ValType<8> { using type = uint64_t; };
 
+#ifndef SPB_SORT_IPT
+#define SPB_SORT_IPT 15
+#endif
+#ifndef SPB_SORT_IPT8
+#define SPB_SORT_IPT8 10
+#endif
+#ifndef SPB_SORT_LBW
+#define SPB_SORT_LBW 4
+#endif
+
 template <bool K32, int VB>
 struct PassCfg {
-    static constexpr int kIPT = VB == 8 ? 12 : 16;                 // 8-byte values: smaller tiles keep 4 CTAs per SM
+    // items per thread: the largest tile that still lets 4 CTAs (32 warps) share an SM's shared memory --
+    // 3840 elements with values of up to 4 bytes, 2560 with 8-byte values
+    static constexpr int kIPT = (VB == 8 || !K32) ? SPB_SORT_IPT8 : SPB_SORT_IPT;
     static constexpr int kTile = kSNT * kIPT;
     static constexpr int kKeyBytes = K32 ? 4 : 8;
     // dynamic shared memory layout (byte offsets; every array 16-byte aligned)
     static constexpr int oVal = 0;                                  // staged values (TMA destination)
-    static constexpr int oKey = oVal + kTile * (VB ? VB : 0);
+    static constexpr int oKey = oVal + kTile * VB;
     static constexpr int oSrc = oKey + kTile * kKeyBytes;           // u16 source position per sorted slot
-    static constexpr int oDig = oSrc + kTile * 2;        // u8 digit per sorted slot
-    static constexpr int oWhist = oDig + kTile;                     // u16 [8][256]
-    static constexpr int oGoff = oWhist + kSWarps * 256 * 2;        // i64 [256]
+    static constexpr int oDig = oSrc + kTile * 2;                   // u8 digit per sorted slot (first pass of a squeezed sort)
+    static constexpr int oWhist = oDig + kTile;                     // u32 [8][256]: counters, then slot offsets
+    static constexpr int oGoff = oWhist + kSWarps * 256 * 4;        // i64 [256]
     static constexpr int oPoff = oGoff + 256 * 8;                   // u64 [256] previous pass's offsets (squeeze)
-    static constexpr int oDstart = oPoff + 256 * 8;                 // i32 [256]
-    static constexpr int oMisc = oDstart + 256 * 4;                 // scan partials, mbarrier
+    static constexpr int oMisc = oPoff + 256 * 8;                   // scan partials, mbarrier
     static constexpr int kTotal = oMisc + 128;
-    // what shared memory allows; 64-bit packed keys take 32 more registers per thread
-    static constexpr int kMinCtas = (K32 && (227 * 1024) / (kTotal + 1024) >= 4) ? 4 : ((227 * 1024) / (kTotal + 1024) >= 3 ? 3 : 2);
+    static constexpr int kFit = (227 * 1024) / (kTotal + 1024);     // CTAs per SM that shared memory allows
+#ifndef SPB_SORT_MAXCTAS
+#define SPB_SORT_MAXCTAS 4
+#endif
+    static constexpr int kCap = K32 ? SPB_SORT_MAXCTAS : 3;         // 64-bit packed keys take more registers
+    static constexpr int kMinCtas = kFit < kCap ? kFit : kCap;
 };
 
 // digit an element at global position `pos` of a pass's input had in the PREVIOUS pass: the input is
@@ -192,6 +224,21 @@ __device__ __forceinline__ unsigned digit_of_position(const uint64_t* s_poff, in
     return (unsigned)(lo - 1);
 }
 
+// lanes of the warp holding the same digit of `nbits` <= 8 bits: one ballot per bit (MATCH.ANY issues about
+// once per 20 cycles per SM, which is what bounded the ranking when it was used here)
+__device__ __forceinline__ unsigned match_digit(unsigned d, int nbits) {
+    unsigned peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        if (b < nbits) {                           // uniform
+            const bool bit = (d >> b) & 1u;
+            const unsigned bal = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? bal : ~bal;
+        }
+    }
+    return peers;
+}
+
 template <bool FIRST, bool LAST, bool K32, int VB>
 __global__ void __launch_bounds__(kSNT, PassCfg<K32, VB>::kMinCtas) radix_pass_kernel(const PassParams p) {
     using C = PassCfg<K32, VB>;
@@ -203,10 +250,9 @@ __global__ void __launch_bounds__(kSNT, PassCfg<K32, VB>::kMinCtas) radix_pass_k
     KS* const s_key = reinterpret_cast<KS*>(smem + C::oKey);
     uint16_t* const s_src = reinterpret_cast<uint16_t*>(smem + C::oSrc);
     uint8_t* const s_dig = reinterpret_cast<uint8_t*>(smem + C::oDig);
-    uint16_t* const s_whist = reinterpret_cast<uint16_t*>(smem + C::oWhist);
+    uint32_t* const s_whist = reinterpret_cast<uint32_t*>(smem + C::oWhist);
     int64_t* const s_goff = reinterpret_cast<int64_t*>(smem + C::oGoff);
     uint64_t* const s_poff = reinterpret_cast<uint64_t*>(smem + C::oPoff);
-    int* const s_dstart = reinterpret_cast<int*>(smem + C::oDstart);
     int* const s_scan = reinterpret_cast<int*>(smem + C::oMisc);              // [8]
     uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + C::oMisc + 64);
 
@@ -216,14 +262,16 @@ __global__ void __launch_bounds__(kSNT, PassCfg<K32, VB>::kMinCtas) radix_pass_k
     const int64_t base = tile * kTile;
     const int items = (int)((p.n - base) < kTile ? (p.n - base) : kTile);
     const int wbase = warp * 32 * kIPT;
-    uint16_t* const my_hist = s_whist + warp * 256;
+    uint32_t* const my_hist = s_whist + warp * 256;
+    const unsigned dmask = (unsigned)p.bins - 1u;
+    const int nbits = 32 - __clz(dmask);
+    // the first pass of a squeezed sort stages keys that no longer hold the digit: it is kept beside them
+    const bool keep_digit = FIRST && !LAST && p.squeeze;
+    const bool keep_src = VB != 0 || (!FIRST && p.squeeze);
 
     // the warp's private digit counters
-    {
-        uint32_t* z = reinterpret_cast<uint32_t*>(my_hist);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) z[i * 32 + lane] = 0;
-    }
+    for (int i = 0; i < 8; ++i) my_hist[i * 32 + lane] = 0;
     bool tma_vals = false;
     if constexpr (VB != 0) {
         tma_vals = p.vals_aligned && items == kTile;
@@ -232,7 +280,9 @@ __global__ void __launch_bounds__(kSNT, PassCfg<K32, VB>::kMinCtas) radix_pass_k
             fence_mbar_init();
         }
     }
+    SPB_STAMP(0);
     cudaGridDependencySynchronize();               // keys, values and offsets come from the previous launches
+    SPB_STAMP(1);
     if constexpr (VB != 0) {
         const VT* vin = reinterpret_cast<const VT*>(p.vals_in) + base;
         if (tma_vals) {
@@ -246,14 +296,15 @@ __global__ void __launch_bounds__(kSNT, PassCfg<K32, VB>::kMinCtas) radix_pass_k
     }
 
     // ---- load, (re-key + pack), digit ---------------------------------------------------------
+    // Elements past the end of the array (last tile only) get the largest digit: they are the last
+    // elements of the tile, so they rank behind everything real and are never written out.
     KS key[kIPT];
-    uint32_t dr[kIPT];                             // digit | rank << 8
-    const unsigned dmask = (unsigned)p.bins - 1u;
+    uint32_t dr[kIPT];                             // digit, later digit | slot << 8
 #pragma unroll
     for (int k = 0; k < kIPT; ++k) {
         const int e = wbase + k * 32 + lane;
         key[k] = 0;
-        dr[k] = 0;
+        dr[k] = dmask;
         if (e < items) {
             if constexpr (FIRST) {
                 const int64_t raw = __ldcs(reinterpret_cast<const int64_t*>(p.keys_in) + base + e);
@@ -274,25 +325,29 @@ __global__ void __launch_bounds__(kSNT, PassCfg<K32, VB>::kMinCtas) radix_pass_k
         }
     }
     __syncwarp();
+    SPB_STAMP(2);
 
     // ---- tile-local stable ranking: per warp, item rows in order, lanes in order inside a row ----
+    // Lanes holding the same digit find each other (eight ballots); the first of them bumps the warp's
+    // counter by the group size with a shared-memory atomic and everybody reads the old value back from
+    // it.  The kIPT atomics of a warp are independent instructions (the counters see them in program
+    // order), so their latencies overlap instead of forming a read-modify-write chain.
+    {
+        uint32_t old[kIPT];
 #pragma unroll
-    for (int k = 0; k < kIPT; ++k) {
-        const int e = wbase + k * 32 + lane;
-        const bool valid = e < items;
-        const unsigned d = dr[k];
-        // lanes holding the same digit (invalid lanes get a private value)
-        unsigned peers = __match_any_sync(0xffffffffu, valid ? d : (0x100u | (unsigned)lane));
-        if (!valid) peers = 0;
-        const int leader = peers ? (__ffs(peers) - 1) : lane;
-        unsigned old = 0;
-        if (valid && lane == leader) {
-            old = my_hist[d];
-            my_hist[d] = (uint16_t)(old + (unsigned)__popc(peers));
+        for (int k = 0; k < kIPT; ++k) {
+            const unsigned d = dr[k];
+            const unsigned peers = match_digit(d, nbits);
+            const int leader = __ffs(peers) - 1;
+            old[k] = 0;
+            if (lane == leader) old[k] = atomicAdd(my_hist + d, (unsigned)__popc(peers));
+            dr[k] = d | ((unsigned)leader << 8) | ((unsigned)__popc(peers & lt_mask) << 13);
         }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        dr[k] = d | ((old + (unsigned)__popc(peers & lt_mask)) << 8);
-        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+            const unsigned o = __shfl_sync(0xffffffffu, old[k], (dr[k] >> 8) & 31u);
+            dr[k] = (dr[k] & 255u) | ((o + (dr[k] >> 13)) << 8);
+        }
     }
 
     // squeeze: which digit of the previous pass does this tile hold?  (uniform for almost every tile)
@@ -306,22 +361,25 @@ __global__ void __launch_bounds__(kSNT, PassCfg<K32, VB>::kMinCtas) radix_pass_k
             prev_inside = o > (uint64_t)base && o < (uint64_t)(base + items);
         }
     }
+    SPB_STAMP(3);
     const int n_le = __syncthreads_count(prev_le);                   // (1) every warp's counters are final
+    SPB_STAMP(4);
     const unsigned dprev_first = (unsigned)(n_le - 1);
 
-    // ---- per digit (thread d): exclusive offsets across warps, tile count, look-back -------------
+    // ---- per digit (thread d): tile count, exclusive offsets across warps and digits -----------------
+    unsigned cw[kSWarps];
     unsigned sum = 0;
-    {
-        const int d = tid;
 #pragma unroll
-        for (int w = 0; w < kSWarps; ++w) {
-            const unsigned t = s_whist[w * 256 + d];
-            s_whist[w * 256 + d] = (uint16_t)sum;
-            sum += t;
-        }
+    for (int w = 0; w < kSWarps; ++w) {
+        cw[w] = s_whist[w * 256 + tid];
+        sum += cw[w];
     }
+    // the padding of the last tile must not reach the successors' offsets (there are none) -- but keep the
+    // published count exact anyway
+    if (tid == (int)dmask) sum -= (unsigned)(kTile - items);
     uint64_t* const st = p.state + tile * p.bins + tid;
     if (tid < p.bins) st_state(st, pack_state(tile == 0 ? kStPrefix : kStAgg, p.epoch, sum));
+    if (tid == (int)dmask) sum += (unsigned)(kTile - items);
     // block exclusive scan of `sum` over the digits
     int incl = (int)sum;
 #pragma unroll
@@ -336,41 +394,53 @@ __global__ void __launch_bounds__(kSNT, PassCfg<K32, VB>::kMinCtas) radix_pass_k
     for (int w = 0; w < kSWarps; ++w)
         if (w < warp) wofs += s_scan[w];
     const int dstart = wofs + incl - (int)sum;
-    s_dstart[tid] = dstart;
-    // the predecessors' words for the first round of the look-back are requested now; they are looked at
-    // after the exchange below
-    constexpr int kLB = 4;                                           // look-back words in flight per digit
-    uint64_t lb[kLB];
-    if (tile > 0 && tid < p.bins) {
+    // slot of the first element of (warp w, digit d) in the digit-sorted tile
+    {
+        unsigned run = (unsigned)dstart;
 #pragma unroll
-        for (int j = 0; j < kLB; ++j) {
-            const int64_t tt = tile - 1 - j;
-            lb[j] = tt >= 0 ? ld_state(p.state + tt * p.bins + tid) : pack_state(kStPrefix, p.epoch, 0);
+        for (int w = 0; w < kSWarps; ++w) {
+            s_whist[w * 256 + tid] = run;
+            run += cw[w];
         }
     }
-    __syncthreads();                                                 // (3) s_dstart and the warp prefixes are in place
+    if (tid == (int)dmask) sum -= (unsigned)(kTile - items);
+    SPB_STAMP(5);
+    __syncthreads();                                                 // (3) the slot offsets are in place
+    SPB_STAMP(6);
 
     // ---- exchange through shared memory into digit order ------------------------------------------
 #pragma unroll
     for (int k = 0; k < kIPT; ++k) {
         const int e = wbase + k * 32 + lane;
-        if (e < items) {
-            const unsigned d = dr[k] & 255u;
-            const int r = s_dstart[d] + (int)my_hist[d] + (int)(dr[k] >> 8);
-            s_key[r] = key[k];
-            s_dig[r] = (uint8_t)d;
-            // source position: where the scatter finds the value, and (squeeze) what recovers the previous digit
-            if (VB != 0 || (!FIRST && p.squeeze)) s_src[r] = (uint16_t)e;
-        }
+        const unsigned d = dr[k] & 255u;
+        const int r = (int)my_hist[d] + (int)(dr[k] >> 8);
+        s_key[r] = key[k];
+        if (keep_digit) s_dig[r] = (uint8_t)d;
+        if (keep_src) s_src[r] = (uint16_t)e;
     }
+    SPB_STAMP(7);
 
     // ---- per-digit look-back -> global offset of every digit's run ----------------------------------
+    // SPB_SORT_LBW predecessors are requested per round.  Every round reads bins x SPB_SORT_LBW words per
+    // tile through L2: 4 measured best (2: 1 % slower, 8: 3 %, 16: 15 % -- the words of a wide window are as
+    // many bytes as the tile's payload).
     if (tid < p.bins) {
         uint64_t excl = 0;
+#ifdef SPB_SORT_NOLB
+        if (false) {                               // timing experiment only: results are wrong
+#else
         if (tile > 0) {
+#endif
+            constexpr int kLB = SPB_SORT_LBW;
             int64_t t = tile - 1;
             bool done = false;
             while (!done && t >= 0) {
+                uint64_t lb[kLB];
+#pragma unroll
+                for (int j = 0; j < kLB; ++j) {
+                    const int64_t tt = t - j;
+                    lb[j] = tt >= 0 ? ld_state(p.state + tt * p.bins + tid) : pack_state(kStPrefix, p.epoch, 0);
+                }
 #pragma unroll
                 for (int j = 0; j < kLB; ++j) {
                     if (!done) {
@@ -384,34 +454,30 @@ __global__ void __launch_bounds__(kSNT, PassCfg<K32, VB>::kMinCtas) radix_pass_k
                     }
                 }
                 t -= kLB;
-                if (!done && t >= 0) {
-#pragma unroll
-                    for (int j = 0; j < kLB; ++j) {
-                        const int64_t tt = t - j;
-                        lb[j] = tt >= 0 ? ld_state(p.state + tt * p.bins + tid) : pack_state(kStPrefix, p.epoch, 0);
-                    }
-                }
             }
             st_state(st, pack_state(kStPrefix, p.epoch, excl + sum));
         }
         s_goff[tid] = (int64_t)(p.off[tid] + excl) - dstart;
     }
+    SPB_STAMP(8);
     __syncthreads();                                                 // (4) sorted tile + offsets complete
+    SPB_STAMP(9);
     if constexpr (VB != 0) {
         if (tma_vals) mbar_wait(bar, 0);
     }
 
+    SPB_STAMP(10);
     // ---- run-coalesced scatter: slot q of the sorted tile goes to goff[digit] + q --------------------
     VT* const vout = reinterpret_cast<VT*>(p.vals_out);
-#pragma unroll 4
+#pragma unroll 5
     for (int j = 0; j < kIPT; ++j) {
         const int q = j * kSNT + tid;
         if (q < items) {
-            const unsigned d = s_dig[q];
-            const int64_t dst = s_goff[d] + q;
             const KS ks = s_key[q];
+            const unsigned d = keep_digit ? (unsigned)s_dig[q] : ((unsigned)(ks >> p.in_shift) & dmask);
+            const int64_t dst = s_goff[d] + q;
             [[maybe_unused]] unsigned src = 0;
-            if constexpr (VB != 0) src = s_src[q];
+            if (keep_src) src = s_src[q];
             if constexpr (FIRST && !LAST) {
                 reinterpret_cast<KS*>(p.keys_out)[dst] = ks;
             } else if constexpr (FIRST && LAST) {
@@ -419,7 +485,6 @@ __global__ void __launch_bounds__(kSNT, PassCfg<K32, VB>::kMinCtas) radix_pass_k
             } else {
                 uint64_t full = (uint64_t)ks;
                 if (p.squeeze) {
-                    if constexpr (VB == 0) src = s_src[q];
                     const unsigned dprev = any_inside ? digit_of_position(s_poff, p.prev_bins, (uint64_t)(base + src))
                                                       : dprev_first;
                     // [hi | this digit | lo] -> re-insert the previous digit below this one
@@ -438,6 +503,7 @@ __global__ void __launch_bounds__(kSNT, PassCfg<K32, VB>::kMinCtas) radix_pass_k
             if constexpr (VB != 0) vout[dst] = s_val[src];
         }
     }
+    SPB_STAMP(11);
 }
 
 // no digits to sort: just re-key (and copy the values)
@@ -601,6 +667,12 @@ int run_sort(const int64_t* idx, const void* val, int64_t n, const Rekey& rk, ui
 using namespace spb;
 
 extern "C" {
+
+#ifdef SPB_SORT_TIMING
+int spb_debug_sort_timing(unsigned long long* buf) {
+    return (int)cudaMemcpyToSymbol(g_sort_timing, &buf, sizeof(buf));
+}
+#endif
 
 int spb_rekey_sort(int dtype, const int64_t* idx, const void* val, int64_t n, int ndim,
                    const int64_t* in_strides, const int64_t* out_strides, int64_t sort_divisor, int sort_bits,
