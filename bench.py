@@ -20,9 +20,15 @@ each, 256 MB of operands: larger than L2, so nothing is re-used between steps) -
                restated in oracle/) timed on this box's host cores (single-threaded: the
                reference has no threading)
 
-N > 1: weak scaling.  The array is range-partitioned on its flat index (contiguous
-blocks of axis 0), rank r owns an equally sized shard; co-partitioned ``a*b`` and the
-axis-2 sum need no collective, so ranks only meet at the barriers.
+N > 1: weak scaling through ``sparray_b200.sharded.ShardedFlatSparray``.  ONE global array of shape
+(256*N, 256, 256, 64) is range-partitioned on its flat index by SAMPLED splitters (quantiles of an
+all-gathered sample of the stored indices, snapped to whole output rows of the axis-2 sum); both operands
+share the splitters, so ``a*b`` and the axis-2 sum need no collective and ranks
+only meet at the barriers.  Beside the headline every N (1 included) also runs BASELINE config[4] at its
+stated per-GPU size -- the co-partitioned union ``a+b`` of two (128*N, 1024, 1024, 256) float32 arrays with
+250 M stored elements per operand per GPU (2 G per operand at N=8), device-generated, sampled splitters --
+and, for N > 1, the same with ``b`` misaligned (NCCL repartition and the fused NVLink peer-load merge):
+``config4_union`` in the JSON line.
 """
 import argparse
 import json
@@ -47,6 +53,14 @@ NCU_TRAFFIC_BYTES = 201019136   # 195.90 MB read + 5.12 MB written
 NCU_TRAFFIC_SOURCE = ("profiles/r1_setop_intersect_final_ncu_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum of "
                       "setop_kernel<float,float,INTERSECT> (69 % of the call's GPU time; the partition and reorder "
                       "launches were not captured with --set full)")
+
+
+def bench_config(na, nb):
+    """The `config` object of the JSON line -- the SAME dict in both arms (ours / --impl reference)."""
+    return {"workload": "BASELINE config[1]: (256,256,256,64) float32, 1% density, c=a*b (intersection) then "
+                        "c.sum(axis=2); one such range shard per GPU (weak scaling)",
+            "shape": list(SHAPE), "density": DENSITY, "value_dtype": "float32", "operand_seeds": [1, 2],
+            "nnz_a": int(na), "nnz_b": int(nb)}
 
 
 def load_oracle():
@@ -166,8 +180,7 @@ def run_reference(args, rank):
         "value": val, "unit": "Gnnz/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE config[1]: (256,256,256,64) float32, 1% density, a*b then sum(axis=2)",
-                   "nnz_a": len(ai), "nnz_b": len(bi)},
+        "config": bench_config(len(ai), len(bi)),
         "cpu_baseline": {"value": val, "unit": "Gnnz/s", "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "Gnnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -180,6 +193,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-ops", action="store_true", help="skip the per-op breakdown (other configs)")
+    ap.add_argument("--eager", action="store_true", help="time plain API calls (never replay the captured step)")
+    ap.add_argument("--graph", action="store_true", help="always replay the step captured into a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.steps is None:
@@ -234,10 +249,40 @@ def main():
     host = [torch.from_numpy(x).pin_memory() for x in (ai, av, bi, bv)]
     A = sp.FlatSparray(host[0].cuda(), host[1].cuda(), shape=SHAPE, is_canonical=True)
     B = sp.FlatSparray(host[2].cuda(), host[3].cuda(), shape=SHAPE, is_canonical=True)
+    sharded_note = None
+    if world > 1:
+        # ONE global (256*N, 256, 256, 64) array: rank r generated block r; the shards are then re-cut at
+        # SAMPLED splitters (snapped to whole output rows of the axis-2 sum) shared by both operands --
+        # untimed setup, it goes through the NCCL exchange of ShardedFlatSparray.repartition
+        from sparray_b200 import sharded as sh
+        size = int(np.prod(SHAPE))
+        gshape = (SHAPE[0] * world,) + tuple(SHAPE[1:])
+        even = [r * size for r in range(world + 1)]
+        a0 = sh.ShardedFlatSparray(A.indices + rank * size, A.data, gshape, even)
+        b0 = sh.ShardedFlatSparray(B.indices + rank * size, B.data, gshape, even)
+        both = torch.cat([a0.indices, b0.indices]).sort().values
+        cuts = sh.sampled_splitters(both, gshape, samples_per_rank=4096, align=SHAPE[2] * SHAPE[3])
+        A_sh, B_sh = a0.repartition(cuts), b0.repartition(cuts)
+        del a0, b0, both
+        na, nb = A_sh.nnz_local, B_sh.nnz_local           # what this rank merges per step
+        sharded_note = {"class": "ShardedFlatSparray", "global_shape": list(gshape), "splitters": "sampled (4096 "
+                        "samples per rank of the merged index stream, all-gathered; snapped down to multiples of "
+                        "%d = one output row of sum(axis=2))" % (SHAPE[2] * SHAPE[3]),
+                        "nnz_local_a_b": [na, nb], "collectives_in_step": 0}
 
-    def step():
-        c = A * B
-        return c, c.sum(axis=2)
+        def step():
+            c = A_sh * B_sh
+            return c, c.sum(axis=2)
+
+        def resolve(c, s):
+            return s.nnz_local
+    else:
+        def step():
+            c = A * B
+            return c, c.sum(axis=2)
+
+        def resolve(c, s):
+            return s.nnz
 
     # ---- value: operands resident in HBM -------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -250,11 +295,46 @@ def main():
     prime = min(args.steps, 100)
     for _ in range(prime):
         c, s = step()
-    s.nnz
+    resolve(c, s)
     torch.cuda.synchronize()
     for _ in range(args.warmup):
         c, s = step()
-    s.nnz
+    resolve(c, s)
+    # ---- the step as a CUDA graph: captured ONCE from the same public-API calls (the library is
+    # capture-safe: a captured launch wipes the look-back words it uses with a memset node of its own), then
+    # one cudaGraphLaunch per step instead of ~60 us of Python.  --eager times the plain calls instead.
+    graph, launches_per_step, submission_probe = None, None, None
+    if not args.eager:
+        cap = torch.cuda.Stream()
+        with torch.cuda.stream(cap):
+            for _ in range(3):                       # scratch of the capture stream's workspace gets its size
+                c, s = step()
+            resolve(c, s)
+        cap.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        l0 = lib.spb_launch_count()
+        with torch.cuda.graph(graph, stream=cap):
+            c, s = step()
+        launches_per_step = int(lib.spb_launch_count() - l0)
+        for _ in range(args.warmup):
+            graph.replay()
+        torch.cuda.synchronize()
+        if not args.graph:
+            # auto: whichever submission is faster HERE (max over ranks) -- plain calls keep their programmatic
+            # dependent launches and win on an idle host; replays win when N ranks' interpreters share the cores
+            def probe(fn, reps=50):
+                barrier()
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for _ in range(reps):
+                    r = fn()
+                p1.record()
+                torch.cuda.synchronize()
+                return max_over_ranks(p0.elapsed_time(p1) / reps)
+            t_eager, t_graph = probe(step), probe(graph.replay)
+            submission_probe = {"eager_ms": t_eager, "graph_ms": t_graph}
+            if t_eager <= t_graph:
+                graph = None
     barrier()
     sampler.mark()
     launches0 = lib.spb_launch_count()
@@ -266,13 +346,18 @@ def main():
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             trace.append((ev, time.perf_counter()))
-        c, s = step()
+        if graph is not None:
+            graph.replay()
+        else:
+            c, s = step()
     if trace is not None:
         trace.append((e1, time.perf_counter()))
-    s.nnz          # element counts stay on the device between steps; the last result is resolved in the timed region
+    resolve(c, s)  # element counts stay on the device between steps; the last result is resolved in the timed region
     e1.record()
     barrier()
     launches = lib.spb_launch_count() - launches0
+    if graph is not None:
+        launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     if trace is not None:
@@ -281,8 +366,16 @@ def main():
         top = sorted(range(args.steps), key=lambda i: -dev[i])[:5]
         sys.stderr.write("trace: total %.3f ms; slowest device steps %s; host %s\n" % (
             e0.elapsed_time(e1), [(i, round(dev[i], 3)) for i in top], [(i, round(hst[i], 3)) for i in top]))
-    value = world * (na + nb) / (ms_step * 1e-3) / 1e9
-    nout = c.nnz
+    n_in = na + nb
+    if world > 1:
+        t = torch.tensor([n_in], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        n_in_total = int(t.item())
+    else:
+        n_in_total = n_in
+    value = n_in_total / (ms_step * 1e-3) / 1e9
+    nout_step = c.nnz if world == 1 else c.nnz_local
+    na, nb = A.nnz, B.nnz                 # from here on: this rank's own block again (e2e, roofline, side lines)
 
     # ---- e2e: pinned host buffers -> public API -> host result -----------------------------------
     def e2e_step():
@@ -304,7 +397,7 @@ def main():
     barrier()
     h2d = sum(t.numel() * t.element_size() for t in host)
     d2h = ri.numel() * 8 + rd.numel() * 8
-    e2e_value = world * (na + nb) / (e2e_ms * 1e-3) / 1e9
+    e2e_value = n_in_total / (e2e_ms * 1e-3) / 1e9
 
     # ---- roofline: the fused intersection kernel alone, CUDA events on its launch stream -----------
     cap = min(na, nb)
@@ -326,6 +419,7 @@ def main():
         b_.record()
     torch.cuda.synchronize()
     k_ms = float(np.mean([a_.elapsed_time(b_) for a_, b_ in evs]))
+    nout = int(cnt.item())
     alg_bytes = (na + nb) * 8 + nout * (4 + 4) + nout * (8 + 4)
     peak, peak_src = hbm_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
@@ -349,6 +443,16 @@ def main():
         except Exception as exc:  # never let the side measurement take the headline line down
             sharded = {"error": str(exc).splitlines()[0][:300]}
 
+    # ---- BASELINE config[4] at its stated per-GPU size: sharded union a+b, 250 M nnz per operand per GPU -----
+    config4 = None
+    if not args.no_ops:
+        del A, B
+        torch.cuda.empty_cache()
+        try:
+            config4 = config4_union(sp, torch, dist, rank, world, barrier, max_over_ranks, peak)
+        except Exception as exc:  # never let the side measurement take the headline line down
+            config4 = {"error": str(exc).splitlines()[0][:300]}
+
     # ---- CPU baseline beside it (rank 0, N=1) ---------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1:
@@ -371,14 +475,18 @@ def main():
             "value": value, "unit": "Gnnz/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE config[1]: (256,256,256,64) float32, 1% density, c=a*b (intersection) "
-                                   "then c.sum(axis=2)", "nnz_a": na, "nnz_b": nb, "nnz_out": nout,
-                       "per_gpu_shard": "one config[1]-sized range shard per GPU, co-partitioned (no collective)",
-                       "l2": "operands (256 MB per GPU) exceed the 126 MB L2; no flush needed",
-                       "sync": "steps are enqueued back to back: element counts stay on the device (lazily counted "
-                               "results); the last step's result is resolved (count read back, buffers trimmed) "
-                               "inside the timed region",
-                       "untimed_setup_steps": prime},
+            "config": bench_config(na, nb),
+            "notes": {"nnz_out_of_the_product": nout_step, "input_nnz_all_ranks": n_in_total,
+                      "per_gpu_shard": "one config[1]-sized range shard per GPU, co-partitioned (no collective)",
+                      "l2": "operands (256 MB per GPU) exceed the 126 MB L2; no flush needed",
+                      "sync": "steps are enqueued back to back: element counts stay on the device (lazily counted "
+                              "results); the last step's result is resolved (count read back, buffers trimmed) "
+                              "inside the timed region",
+                      "step_submission": "eager API calls" if graph is None else
+                                         "the step's public-API calls captured once into a CUDA graph (torch.cuda.graph), "
+                                         "one replay per step; %d kernel launches per replay" % launches_per_step,
+                      "submission_probe_ms": submission_probe,
+                      "untimed_setup_steps": prime, "sharded": sharded_note},
             "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Gnnz/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
@@ -390,6 +498,8 @@ def main():
             out["ops"] = ops
         if sharded is not None:
             out["sharded_exchange"] = sharded
+        if config4 is not None:
+            out["config4_union"] = config4
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -489,6 +599,91 @@ def sharded_exchange(torch, dist, A, B, rank, world, barrier, max_over_ranks):
                     "all_to_all_single (NCCL); received segments are already in order, no merge.  peer loads = "
                     "ShardedFlatSparray.binop_peer: one all-gather of cut positions, then one fused merge launch "
                     "per overlapping source rank reading that rank's slice from symmetric memory over NVLink"}
+
+
+def config4_union(sp, torch, dist, rank, world, barrier, max_over_ranks, peak):
+    """BASELINE config[4]: union a+b of two 4-D float32 arrays with 250 M stored
+    elements per operand PER GPU -- global shape (128*N, 1024, 1024, 256), 2 G per operand at N=8 -- generated
+    on the device, range-partitioned by sampled splitters, co-partitioned (no collective); then, N > 1, with b
+    cut at splitters shifted by half a shard: NCCL repartition and the fused peer-load merge."""
+    from sparray_b200 import sharded as sh
+    slab = (128, 1024, 1024, 256)
+    size = int(np.prod(slab))
+    n_per = 250_000_000
+    gshape = (slab[0] * world,) + slab[1:]
+    ai, av = synth_sorted(torch, n_per, size, torch.float32, 11 + 100 * rank)
+    bi, bv = synth_sorted(torch, n_per, size, torch.float32, 12 + 100 * rank)
+
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            r = fn()
+            del r
+        ts = []
+        for _ in range(reps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(max_over_ranks(e0.elapsed_time(e1)))
+            del r
+        return float(np.median(ts))
+
+    if world == 1:
+        A = sp.FlatSparray(ai, av, shape=gshape, is_canonical=True)
+        B = sp.FlatSparray(bi, bv, shape=gshape, is_canonical=True)
+        na, nb = A.nnz, B.nnz
+        nout = (A + B).nnz
+        ms = timed(lambda: A + B)
+        tot_in, tot_out = na + nb, nout
+        extra = {}
+    else:
+        even = [r * size for r in range(world + 1)]
+        ai += rank * size
+        bi += rank * size
+        a0 = sh.ShardedFlatSparray(ai, av, gshape, even)
+        b0 = sh.ShardedFlatSparray(bi, bv, gshape, even)
+        cuts = sh.sampled_splitters(a0.indices, gshape, samples_per_rank=4096)
+        A, B = a0.repartition(cuts), b0.repartition(cuts)
+        del a0, b0, ai, av, bi, bv
+        torch.cuda.empty_cache()
+        na, nb = A.nnz_local, B.nnz_local
+        nout = (A + B).nnz_local
+        ms = timed(lambda: A + B)
+        t = torch.tensor([na + nb, nout], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        tot_in, tot_out = int(t[0].item()), int(t[1].item())
+        # b misaligned: its splitters sit half a shard to the right of a's
+        shifted = [cuts[0]] + [(cuts[r] + cuts[r + 1]) // 2 for r in range(world - 1)] + [cuts[-1]]
+        B_sh = B.repartition(shifted)
+        moved = int(((B_sh.indices < cuts[rank]) | (B_sh.indices >= cuts[rank + 1])).sum().item())
+        t_rep = timed(lambda: B_sh.repartition(cuts), reps=3, warm=1)
+        t_add = timed(lambda: (A + B_sh).nnz_local, reps=3, warm=1)
+        mv = torch.tensor([moved], dtype=torch.int64, device="cuda")
+        dist.all_reduce(mv)
+        extra = {"misaligned_b": {"what": "b cut at splitters shifted by half a shard: a+b = repartition(b) + local union",
+                                  "repartition_ms": t_rep, "add_with_repartition_ms": t_add,
+                                  "elements_crossing_gpus": int(mv.item()),
+                                  "nvlink_GBps_per_gpu_send": int(mv.item()) / world * 12 / (t_rep * 1e-3) / 1e9,
+                                  "nvlink_peak_GBps_per_direction": 900.0, "nvlink_measured_peer_copy_GBps": 770.0}}
+        try:
+            b_pub = B_sh.publish()
+            t_peer = timed(lambda: A.binop_peer(b_pub, "union", "add").nnz_local, reps=3, warm=1)
+            extra["misaligned_b"]["add_with_peer_loads_ms"] = t_peer
+            b_pub.barrier()
+        except Exception as exc:
+            extra["misaligned_b"]["peer_loads"] = "unavailable: %s" % str(exc).splitlines()[0][:200]
+    alg_bytes_per_gpu = (na + nb + nout) * 12
+    out = {"workload": "BASELINE config[4]: union a+b of two (128*N,1024,1024,256) float32 arrays, 250 M stored elements "
+                       "per operand per GPU, sampled splitters, co-partitioned (no collective), device-generated",
+           "global_shape": list(gshape), "nnz_in_all_gpus": tot_in, "nnz_out_all_gpus": tot_out,
+           "ms": ms, "Gnnz_per_s": tot_in / (ms * 1e-3) / 1e9,
+           "alg_GBps_per_gpu": alg_bytes_per_gpu / (ms * 1e-3) / 1e9,
+           "frac_of_hbm_peak_per_gpu": alg_bytes_per_gpu / (ms * 1e-3) / 1e9 / peak,
+           "timing": "CUDA events around the API call (lazily counted result), max over ranks, median of 5"}
+    out.update(extra)
+    return out
 
 
 def op_breakdown(sp, torch, A, B, peak):

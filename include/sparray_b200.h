@@ -60,7 +60,9 @@ enum spb_error {
     SPB_ERR_BAD_ARG = 10001,        /* null pointer, negative size, unknown enum */
     SPB_ERR_UNSUPPORTED = 10002,    /* dtype/op combination not instantiated */
     SPB_ERR_NO_DEVICE = 10003,      /* no CUDA device: there is no CPU fallback */
-    SPB_ERR_TOO_LARGE = 10004
+    SPB_ERR_TOO_LARGE = 10004,
+    SPB_ERR_CAPTURE = 10005         /* scratch would have to grow while the stream is captured into a CUDA graph:
+                                       run the same call once before capturing */
 };
 
 /* ---- 0. library / workspace ------------------------------------------------ */
@@ -72,7 +74,10 @@ unsigned long long spb_launch_count(void);  /* kernels launched by this library 
 uint64_t spb_debug_fastdiv(uint64_t n, uint64_t d);   /* host copy of the kernels' exact n / d (n < 2^63) */
 
 /* Scratch for tile look-back state etc.  One per stream in flight; grows on
- * demand.  State words are epoch-tagged, so no memset between launches. */
+ * demand.  State words are epoch-tagged, so no memset between launches.
+ * CUDA graphs: every entry point may be captured (cudaStreamBeginCapture / torch.cuda.graph) once the same
+ * call has run eagerly, so that the scratch has its size; a captured launch wipes the state words it uses
+ * with a memset node of its own (an epoch baked into a graph cannot tell one replay from the next). */
 typedef struct spb_workspace spb_workspace;
 int spb_workspace_create(spb_workspace** ws);
 int spb_workspace_destroy(spb_workspace* ws);
@@ -201,8 +206,8 @@ int spb_spmv(int dtype, const int64_t* idx, const void* vals, int64_t n, int64_t
  * the C-order strides in_strides[g] of (merged) axis group g in the old shape
  * (outermost first, in_strides[ndim-1] == 1; out_strides[g] == 0 drops the
  * group; ndim == 0 keeps the keys).  The (new_key, val) pairs are then stably
- * LSD-radix-sorted on the low `sort_bits` bits of new_key / sort_divisor, 8 bits
- * per pass -- the host strips trailing axes that already arrive in order
+ * LSD-radix-sorted on new_key / sort_divisor, which must be < 2^sort_bits, in digits of at most
+ * 8 bits -- the host strips trailing axes that already arrive in order
  * (sparray_b200/_plan.py).  This is np.unravel_index + np.ravel_multi_index +
  * the argsort inside np.unique of transpose (flat.py:109-112,34) and of
  * sum(axis) (flat.py:617-620) in (1 + passes) sweeps with no index temporaries.
@@ -226,6 +231,15 @@ int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val, int64_t n
                        int ndim, const int64_t* in_strides_host, const int64_t* out_strides_host,
                        int64_t cells, int64_t* out_idx, double* out_sums, int64_t* out_count,
                        spb_workspace* ws, spb_stream_t stream);
+
+/* spb_axis_sum_dense restricted to the cells [cell_lo, cell_hi) of the reduced array: accumulators are
+ * only held for that window (a range shard of a sharded array can only touch the rows of its own flat
+ * range).  Elements whose cell falls outside the window are ignored.  out_idx / out_sums:
+ * min(n, cell_hi - cell_lo) slots; emitted keys are absolute cell numbers. */
+int spb_axis_sum_window(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev,
+                        int ndim, const int64_t* in_strides_host, const int64_t* out_strides_host,
+                        int64_t cell_lo, int64_t cell_hi, int64_t* out_idx, double* out_sums, int64_t* out_count,
+                        spb_workspace* ws, spb_stream_t stream);
 
 /* The two halves of spb_axis_sum_dense on caller-owned buffers, for the sharded axis sum of
  * SURVEY.md section 8(e) (dense per-GPU accumulators + all-reduce): acc = cells doubles,

@@ -21,6 +21,8 @@ ai, av = synth(10_700_000, 256 * 256 * 256 * 64, torch.float32, 1)
 A = sp.FlatSparray(ai, av, shape=shape, is_canonical=True)
 print("sum_axis3 (last) f32 10.7M: %.0f us" % t(lambda: A.sum(axis=3)))
 print("sum_axis2 f32 10.7M: %.0f us" % t(lambda: A.sum(axis=2)))
+print("  reduce_by_key(div 64) = last-axis sum without the dense slab: %.0f us" % t(lambda: k.reduce_by_key(ai, av, 64)))
+print("  sum_axis1 f32 10.7M: %.0f us ; sum_axis0: %.0f us" % (t(lambda: A.sum(axis=1)), t(lambda: A.sum(axis=0))))
 print("transpose 3210 f32 10.7M: %.0f us" % t(lambda: A.transpose(3, 2, 1, 0)))
 wi, wv = synth(100_000_000, 10 ** 12, torch.float64, 4)
 W = sp.FlatSparray(wi, wv, shape=(10 ** 6, 10 ** 6), is_canonical=True)

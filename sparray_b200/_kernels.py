@@ -284,36 +284,61 @@ def transpose(idx, val, shape, axes):
 DENSE_SUM_MAX_CELLS = 1 << 26      # 512 MiB of float64 accumulators
 
 
-DENSE_SUM_ANY_N_CELLS = 1 << 22    # below this the dense path is taken whatever the element count
+@functools.lru_cache(maxsize=8)
+def _l2_resident_cells(device_index):
+    """Cells of the dense accumulator slab (8-byte sum + 1 flag byte each) that fit in HALF of this device's
+    L2: below this the dense path is taken whatever the element count -- every atomic then hits L2 and the
+    compaction pass reads the flags from it."""
+    l2 = 126 << 20                                  # B200; the planning helpers also run without a device
+    if device_index >= 0 and torch.cuda.is_available():
+        props = torch.cuda.get_device_properties(device_index)
+        l2 = int(getattr(props, "L2_cache_size", 0)) or l2
+    return max(l2 // 2 // 9, 1 << 16)
+
+
+def _cur_dev():
+    return torch._C._cuda_getDevice() if torch.cuda.is_available() else -1
 
 
 def dense_sum_cells(shape, axis):
     """Cell count of sum(axis)'s result if the dense-accumulator path applies whatever nnz is, else 0."""
     from . import _plan
     cells = _plan.prod(shape) // max(int(shape[axis]), 1)
-    return cells if 0 < cells <= DENSE_SUM_ANY_N_CELLS else 0
+    return cells if 0 < cells <= _l2_resident_cells(_cur_dev()) else 0
 
 
-def sum_axis(idx, val, shape, axis, n_dev=None):
+def _use_dense(n, cells, last, n_dev):
+    if n_dev is not None:
+        return True
+    if not n or cells > DENSE_SUM_MAX_CELLS:
+        return False
+    return cells <= (4 if last else 64) * n + _l2_resident_cells(_cur_dev())
+
+
+def sum_axis(idx, val, shape, axis, n_dev=None, window=None):
     """(new sorted unique flat indices, float64 sums, device count or None) -- flat.py:617-625.
     Whenever the reduced array is small enough to hold densely (and not much sparser than the input):
     warp-aggregated float64 atomics into a dense accumulator + one compaction pass, no sort, any axis.
     Otherwise: last axis -> segmented reduce over the already sorted keys; other axes -> re-key +
     radix sort + segmented reduce.  The dense path leaves its element count on the device
     (worst-case-sized outputs); n_dev is the device count of a producer that was not read back
-    either (only valid when dense_sum_cells())."""
+    either (only valid when the dense path is certain: dense_sum_cells()).
+    window = (cell_lo, cell_hi): the caller knows that every output cell lies in that range of the
+    reduced array (a range shard of a sharded array): accumulators are only held for the window."""
     from . import _plan
     plan = _plan.axis_sum_plan(shape, axis)
     n = idx.numel()
-    cells = _plan.prod(shape) // max(int(shape[axis]), 1)
+    total_cells = _plan.prod(shape) // max(int(shape[axis]), 1)
+    lo, hi = (0, total_cells) if window is None else (int(window[0]), int(window[1]))
+    cells = hi - lo
     if plan[0] == "last":
-        if n_dev is not None or (n and cells <= DENSE_SUM_MAX_CELLS and cells <= 4 * n + DENSE_SUM_ANY_N_CELLS):
+        if _use_dense(n, cells, True, n_dev):
             # the elements of an output cell are contiguous: warp-aggregated atomics into the dense accumulator
-            return axis_sum_dense(idx, val, [plan[1], 1], [1, 0], cells, n_dev)
+            return axis_sum_dense(idx, val, [plan[1], 1], [1, 0], lo, hi, n_dev)
         return reduce_by_key(idx, val, plan[1]) + (None,)
     _, in_s, out_s, bits = plan
-    if n and cells <= DENSE_SUM_MAX_CELLS and cells <= 64 * n + DENSE_SUM_ANY_N_CELLS:
-        return axis_sum_dense(idx, val, in_s, out_s, cells, n_dev)
+    if _use_dense(n, cells, False, n_dev):
+        return axis_sum_dense(idx, val, in_s, out_s, lo, hi, n_dev)
     assert n_dev is None
     keys, vals = rekey_sort(idx, val, in_s, out_s, 1, bits)
     return reduce_by_key(keys, vals, 1) + (None,)
@@ -329,16 +354,17 @@ def _stride_args(in_strides, out_strides):
     return ndim, ctypes.cast(ins, ctypes.c_void_p), ctypes.cast(outs, ctypes.c_void_p), (ins, outs)
 
 
-def axis_sum_dense(idx, val, in_strides, out_strides, cells, n_dev=None):
+def axis_sum_dense(idx, val, in_strides, out_strides, cell_lo, cell_hi, n_dev=None):
     require_cuda()
     n = idx.numel()
-    cap = min(n, cells)
+    cap = min(n, cell_hi - cell_lo)
     out_idx = torch.empty(cap, dtype=torch.int64, device=idx.device)
     out_sums = torch.empty(cap, dtype=torch.float64, device=idx.device)
     cnt = torch.empty(1, dtype=torch.int64, device=idx.device)
     ndim, ins, outs, _keep = _stride_args(tuple(in_strides), tuple(out_strides))
-    check(lib.spb_axis_sum_dense(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), n, ptr(n_dev), ndim, ins, outs, int(cells),
-                                 ptr(out_idx), ptr(out_sums), ptr(cnt), workspace(), stream()))
+    check(lib.spb_axis_sum_window(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), n, ptr(n_dev), ndim, ins, outs,
+                                  int(cell_lo), int(cell_hi), ptr(out_idx), ptr(out_sums), ptr(cnt), workspace(),
+                                  stream()))
     return out_idx, out_sums, cnt
 
 

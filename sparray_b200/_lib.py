@@ -73,6 +73,7 @@ PROTOTYPES = {
     "spb_reduce_by_key": (c_int, [c_int, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p]),
     "spb_spmv": (c_int, [c_int, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_p]),
     "spb_axis_sum_dense": (c_int, [c_int, c_p, c_p, c_i64, c_p, c_int, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p]),
+    "spb_axis_sum_window": (c_int, [c_int, c_p, c_p, c_i64, c_p, c_int, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p]),
     "spb_axis_accumulate": (c_int, [c_int, c_p, c_p, c_i64, c_int, c_p, c_p, c_i64, c_p, c_p, c_p]),
     "spb_emit_touched": (c_int, [c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p]),
     "spb_getitem_box": (c_int, [c_int, c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),

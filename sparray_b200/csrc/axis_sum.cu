@@ -18,11 +18,19 @@ namespace spb {
 // each run adds the run's sum into its cell with one float64 atomic.
 constexpr int kAccUnroll = 4;
 
+// cell of a stored element inside the accumulator window [cell_lo, cell_lo + cells): -1 when it falls
+// outside (a flat index beyond prod(shape), which resize() permits, must not touch the slab)
+__device__ __forceinline__ int64_t window_cell(int64_t idx, const Rekey& rk, int64_t cell_lo, int64_t cells) {
+    const int64_t c = apply_rekey(idx, rk) - cell_lo;
+    return (uint64_t)c < (uint64_t)cells ? c : -1;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
                                                               int64_t n, const int64_t* __restrict__ n_dev,
                                                               const Rekey rk, double* __restrict__ acc,
-                                                              uint8_t* __restrict__ touched) {
+                                                              uint8_t* __restrict__ touched, const int64_t cell_lo,
+                                                              const int64_t cells) {
     cudaTriggerProgrammaticLaunchCompletion();
     cudaGridDependencySynchronize();   // operands (and n_dev) may come from the previous launch
     if (n_dev) {                       // the producer's count never left the device; n is its upper bound
@@ -36,9 +44,11 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
         // few elements (typically a lazily counted product whose real count is far below its upper bound):
         // one element per thread, no aggregation -- the shortest critical path
         if (gtid < n) {
-            const int64_t key = apply_rekey(__ldcs(idx + gtid), rk);
-            atomicAdd(acc + key, (double)__ldcs(val + gtid));
-            touched[key] = 1;
+            const int64_t key = window_cell(__ldcs(idx + gtid), rk, cell_lo, cells);
+            if (key >= 0) {
+                atomicAdd(acc + key, (double)__ldcs(val + gtid));
+                touched[key] = 1;
+            }
         }
         return;
     }
@@ -56,7 +66,7 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
         }
 #pragma unroll
         for (int u = 0; u < kAccUnroll; ++u)
-            if (key[u] >= 0) key[u] = apply_rekey(key[u], rk);
+            if (key[u] >= 0) key[u] = window_cell(key[u], rk, cell_lo, cells);
 #pragma unroll
         for (int u = 0; u < kAccUnroll; ++u) {
             // runs = maximal stretches of ADJACENT lanes with the same key (equal keys further apart are
@@ -107,7 +117,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) axis_accumulate_runs_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
                                                               int64_t n, const int64_t* __restrict__ n_dev,
                                                               const Rekey rk, double* __restrict__ acc,
-                                                              uint8_t* __restrict__ touched) {
+                                                              uint8_t* __restrict__ touched, const int64_t cell_lo,
+                                                              const int64_t cells) {
     cudaTriggerProgrammaticLaunchCompletion();
     cudaGridDependencySynchronize();   // operands (and n_dev) may come from the previous launch
     if (n_dev) {                       // the producer's count never left the device; n is its upper bound
@@ -129,7 +140,7 @@ __global__ void __launch_bounds__(256) axis_accumulate_runs_kernel(const int64_t
         }
 #pragma unroll
         for (int j = 0; j < kAccItems; ++j)
-            if (key[j] >= 0) key[j] = apply_rekey(key[j], rk);
+            if (key[j] >= 0) key[j] = window_cell(key[j], rk, cell_lo, cells);
         // my runs of adjacent equal cells: all but a single whole-lane run go in atomically right here
         const bool single = key[0] >= 0 && key[0] == key[1] && key[1] == key[2] && key[2] == key[3];
         int64_t cell = -2 - lane;      // negative and distinct: takes no part in the warp's runs
@@ -171,31 +182,28 @@ __global__ void __launch_bounds__(256) axis_accumulate_runs_kernel(const int64_t
 
 // Emits the touched cells in key order and puts every cell it emitted back to zero, so the
 // accumulator slab is all-zero again when the call is over (no memset per call).  One thread owns
-// 64 cells (four 16-byte loads of flag bytes); a tile of 256 threads covers 16 K cells, which keeps
-// the look-back chain short.
+// kSelCells cells (one 16-byte load of flag bytes); a tile of 256 threads covers 4 K cells -- thousands of
+// tiles for the BASELINE shapes, enough to fill the machine -- and the whole block looks back (256
+// predecessor tiles per round), so the chain of tile offsets stays a round or two long.
+constexpr int kSelCells = 16;
+
 __global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict__ acc, uint8_t* __restrict__ touched,
                                                              int64_t cells, int64_t key_base, int64_t* __restrict__ out_idx,
                                                              double* __restrict__ out_val, int64_t* out_count,
                                                              uint64_t* state, uint32_t epoch) {
     const int64_t tile = blockIdx.x;
-    const int64_t first = (tile * 256 + threadIdx.x) * 64;
+    const int64_t first = (tile * 256 + threadIdx.x) * kSelCells;
     cudaGridDependencySynchronize();   // accumulators come from the previous launch
-    unsigned long long bits = 0;
+    unsigned bits = 0;
     if (first < cells) {               // the flag array is padded to a multiple of 64 (the padding stays zero)
         uint4* const flags = reinterpret_cast<uint4*>(touched + first);
-        uint4 raw[4];
+        const uint4 raw = *flags;
+        const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) raw[q] = flags[q];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const unsigned w[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                bits |= (unsigned long long)((w[k >> 2] >> (8 * (k & 3))) & 1u) << (16 * q + k);
-            if (raw[q].x | raw[q].y | raw[q].z | raw[q].w) flags[q] = make_uint4(0, 0, 0, 0);
-        }
+        for (int k = 0; k < 16; ++k) bits |= ((w[k >> 2] >> (8 * (k & 3))) & 1u) << k;
+        if (bits) *flags = make_uint4(0, 0, 0, 0);
     }
-    const int cnt = __popcll(bits);
+    const int cnt = __popc(bits);
     const int64_t off = compact_offset_256<true>(cnt, state, epoch, tile, tile == gridDim.x - 1, out_count);
     // Warp-cooperative emission: the warp's outputs are one contiguous run, written 32 at a time (coalesced
     // whether the cells are nearly all touched or nearly all empty).  Output r of the warp belongs to the
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict_
     }
     const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
     const int64_t warp_off = __shfl_sync(0xffffffffu, off, 0);
-    const int64_t warp_first = first - (int64_t)lane * 64;
+    const int64_t warp_first = first - (int64_t)lane * kSelCells;
     for (int c = 0; c < warp_total; c += 32) {
         const int r = c + lane;
         int owner = 0;
@@ -220,12 +228,10 @@ __global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict_
         }
         owner = owner > 31 ? 31 : owner;
         const int owner_excl = __shfl_sync(0xffffffffu, incl - cnt, owner);
-        const unsigned lo_bits = __shfl_sync(0xffffffffu, (unsigned)bits, owner);
-        const unsigned hi_bits = __shfl_sync(0xffffffffu, (unsigned)(bits >> 32), owner);
+        const unsigned obits = __shfl_sync(0xffffffffu, bits, owner);
         if (r < warp_total) {
-            const int j = r - owner_excl, nlo = __popc(lo_bits);
-            const int k = j < nlo ? (int)__fns(lo_bits, 0, j + 1) : 32 + (int)__fns(hi_bits, 0, j - nlo + 1);
-            const int64_t cell = warp_first + (int64_t)owner * 64 + k;
+            const int k = (int)__fns(obits, 0, r - owner_excl + 1);
+            const int64_t cell = warp_first + (int64_t)owner * kSelCells + k;
             out_idx[warp_off + r] = key_base + cell;
             out_val[warp_off + r] = acc[cell];
             acc[cell] = 0.0;
@@ -238,7 +244,8 @@ __global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict_
 namespace spb {
 
 static int launch_accumulate(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev,
-                             const Rekey& rk, int64_t cells, double* acc, uint8_t* touched, cudaStream_t stream) {
+                             const Rekey& rk, int64_t cell_lo, int64_t cells, double* acc, uint8_t* touched,
+                             cudaStream_t stream) {
     int64_t blocks = ceil_div(n, 256 * kAccUnroll);
     if (blocks > (int64_t)device_sm_count() * 16) blocks = (int64_t)device_sm_count() * 16;
     // long contiguous runs (innermost axis reduced, >= 8 elements per output cell on average): the variant
@@ -247,10 +254,10 @@ static int launch_accumulate(int dtype, const int64_t* idx, const void* val, int
 #define SPB_ACC(T)                                                                                            \
     if (long_runs) {                                                                                          \
         SPB_CUDA_TRY(launch_pdl(axis_accumulate_runs_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, \
-                                idx, (const T*)val, n, n_dev, rk, acc, touched));                             \
+                                idx, (const T*)val, n, n_dev, rk, acc, touched, cell_lo, cells));             \
     } else {                                                                                                  \
         SPB_CUDA_TRY(launch_pdl(axis_accumulate_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, idx, \
-                                (const T*)val, n, n_dev, rk, acc, touched));                                  \
+                                (const T*)val, n, n_dev, rk, acc, touched, cell_lo, cells));                  \
     }                                                                                                         \
     break
     switch (dtype) {
@@ -271,7 +278,7 @@ static int launch_accumulate(int dtype, const int64_t* idx, const void* val, int
 // cells of [0, cells) relative to acc / touched (touched readable up to the next multiple of 64)
 static int launch_select(double* acc, uint8_t* touched, int64_t cells, int64_t key_base, int64_t* out_idx,
                          double* out_sums, int64_t* out_count, spb_workspace* ws, cudaStream_t stream) {
-    const int64_t ntiles = ceil_div(cells, 256 * 64);
+    const int64_t ntiles = ceil_div(cells, 256 * kSelCells);
     if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
     int rc = workspace_reserve(ws, (size_t)ntiles * 8, stream);
     if (rc) return rc;
@@ -286,12 +293,14 @@ static int launch_select(double* acc, uint8_t* touched, int64_t cells, int64_t k
 
 }  // namespace spb
 
-extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev, int ndim,
-                                  const int64_t* in_strides, const int64_t* out_strides, int64_t cells,
-                                  int64_t* out_idx, double* out_sums, int64_t* out_count,
-                                  spb_workspace* ws, spb_stream_t stream) {
+// cells of the reduced array in [cell_lo, cell_hi) only (every element must fall inside; others are ignored)
+static int axis_sum_window(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev, int ndim,
+                           const int64_t* in_strides, const int64_t* out_strides, int64_t cell_lo, int64_t cell_hi,
+                           int64_t* out_idx, double* out_sums, int64_t* out_count, spb_workspace* ws,
+                           cudaStream_t stream) {
     using namespace spb;
-    if (n < 0 || cells < 0 || !out_count) return SPB_ERR_BAD_ARG;
+    if (n < 0 || cell_lo < 0 || cell_hi < cell_lo || !out_count) return SPB_ERR_BAD_ARG;
+    const int64_t cells = cell_hi - cell_lo;
     Rekey rk{};
     if (ndim < 1) return SPB_ERR_BAD_ARG;
     int rc = make_rekey(rk, ndim, in_strides, out_strides);
@@ -303,11 +312,36 @@ extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val
     const int64_t nflags = ceil_div(cells, 64) * 64;
     rc = workspace_reserve_accum(ws, acc_bytes + (size_t)nflags, stream);
     if (rc) return rc;
+    // The slab is only all-zero again once the emitting pass has run: if an earlier call failed between
+    // its two launches, wipe it before anybody adds into it.
+    if (ws->accum_dirty) {
+        SPB_CUDA_TRY(cudaMemsetAsync(ws->accum, 0, ws->accum_bytes, stream));
+        ws->accum_dirty = 0;
+    }
     double* const acc = reinterpret_cast<double*>(ws->accum);
     uint8_t* const touched = reinterpret_cast<uint8_t*>(ws->accum) + acc_bytes;
-    rc = launch_accumulate(dtype, idx, val, n, n_dev, rk, cells, acc, touched, stream);
+    ws->accum_dirty = 1;
+    rc = launch_accumulate(dtype, idx, val, n, n_dev, rk, cell_lo, cells, acc, touched, stream);
     if (rc) return rc;
-    return launch_select(acc, touched, cells, 0, out_idx, out_sums, out_count, ws, stream);
+    rc = launch_select(acc, touched, cells, cell_lo, out_idx, out_sums, out_count, ws, stream);
+    if (rc == SPB_OK) ws->accum_dirty = 0;
+    return rc;
+}
+
+extern "C" int spb_axis_sum_dense(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev, int ndim,
+                                  const int64_t* in_strides, const int64_t* out_strides, int64_t cells,
+                                  int64_t* out_idx, double* out_sums, int64_t* out_count,
+                                  spb_workspace* ws, spb_stream_t stream) {
+    return axis_sum_window(dtype, idx, val, n, n_dev, ndim, in_strides, out_strides, 0, cells, out_idx, out_sums,
+                           out_count, ws, stream);
+}
+
+extern "C" int spb_axis_sum_window(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev,
+                                   int ndim, const int64_t* in_strides, const int64_t* out_strides, int64_t cell_lo,
+                                   int64_t cell_hi, int64_t* out_idx, double* out_sums, int64_t* out_count,
+                                   spb_workspace* ws, spb_stream_t stream) {
+    return axis_sum_window(dtype, idx, val, n, n_dev, ndim, in_strides, out_strides, cell_lo, cell_hi, out_idx,
+                           out_sums, out_count, ws, stream);
 }
 
 // The two halves on caller-owned buffers, for the sharded axis sum (all-reduce of the accumulators
@@ -324,7 +358,7 @@ extern "C" int spb_axis_accumulate(int dtype, const int64_t* idx, const void* va
     if (rc) return rc;
     if (n == 0 || cells == 0) return SPB_OK;
     if (!idx || !val || !acc || !touched) return SPB_ERR_BAD_ARG;
-    return launch_accumulate(dtype, idx, val, n, nullptr, rk, cells, acc, touched, stream);
+    return launch_accumulate(dtype, idx, val, n, nullptr, rk, 0, cells, acc, touched, stream);
 }
 
 // Emit the touched cells of [cell_lo, cell_hi) in key order (keys are absolute cell numbers).

@@ -33,6 +33,9 @@ struct spb_workspace {
     size_t state16_bytes;
     void* accum;          // dense accumulators + flags: all zero between calls (the consumer cleans what it reads)
     size_t accum_bytes;
+    int accum_dirty;      // an accumulate pass was enqueued whose emitting pass was not: wipe before the next use
+    size_t last_state_bytes;     // look-back words / 16-byte entries the call in progress asked for: what a
+    size_t last_state16_bytes;   // captured launch wipes before it runs (see workspace_next_epoch)
 };
 
 namespace spb {

@@ -53,6 +53,7 @@ const char* spb_error_string(int code) {
         case SPB_ERR_UNSUPPORTED: return "dtype/op combination not supported by the CUDA kernels";
         case SPB_ERR_NO_DEVICE: return "no CUDA device (sparray_b200 has no CPU fallback)";
         case SPB_ERR_TOO_LARGE: return "problem too large for one launch";
+        case SPB_ERR_CAPTURE: return "scratch must grow but the stream is being captured: run the call once before capturing";
         default: return cudaGetErrorString((cudaError_t)code);
     }
 }

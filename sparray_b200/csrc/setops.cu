@@ -146,6 +146,7 @@ struct PartitionParams {
     uint64_t* desc;          // [ntiles][kDescWords]
     int* group_cnt;          // intersections: [ngroups] match counters to zero, else null
     int64_t ngroups;
+    double frac_a;           // na / (na + nb): where the proportional guess of a diagonal's split lies
 };
 
 constexpr int64_t kGuessWindow = 8192;
@@ -156,9 +157,14 @@ constexpr int kPartTiles = 15;
 constexpr int kPartThreads = 512;
 constexpr int kGroupTiles = 64;          // intersections: tiles per group counter (see merge_reorder_kernel)
 
-// One warp per diagonal.  Round 1 probes the bracket around the proportional guess (2 lanes) AND 30 points
-// inside it, so for operands of comparable density the search is three dependent rounds of probes (the
-// window shrinks 16384 -> ~550 -> ~18 -> found); anything else falls back to plain 32-ary rounds.
+// One warp per diagonal.  The split is where the two key sequences cross, and sorted flat indices grow
+// close to linearly with their position: so the search INTERPOLATES.  A probe at the current guess g gives
+// delta = a[g] - b[d-1-g]; one step of the split moves a's key up by one average gap of a and b's key down
+// by one of b, so the crossing is about delta / (gap_a + gap_b) positions away.  Two or three such probes
+// (two keys each) land within a few elements of the split, and one window of 32 consecutive candidates
+// (coalesced) pins it down.  ~1 KB of keys per diagonal instead of the ~12 KB a 32-ary search reads -- the
+// partition launch of round 1 moved 60 % as many bytes as the merge itself.  Whatever the data does to the
+// interpolation, every step keeps [lo, hi] a valid bracket and the tail is a plain 32-ary search.
 __device__ __forceinline__ int64_t merge_split_warp(const PartitionParams& p, int64_t w) {
     const int lane = threadIdx.x & 31;
     const int64_t total = p.na + p.nb;
@@ -166,31 +172,37 @@ __device__ __forceinline__ int64_t merge_split_warp(const PartitionParams& p, in
     if (d > total) d = total;
     int64_t lo = d > p.nb ? d - p.nb : 0;
     int64_t hi = d < p.na ? d : p.na;
-    // predicate "the split lies above m": a[m] <= b[d-1-m]; true for m < split, false from the split on
-    if (hi - lo > 4 * kGuessWindow) {
-        const int64_t guess = (int64_t)(((unsigned __int128)(uint64_t)d * (uint64_t)p.na) / (uint64_t)total);
-        int64_t lo2 = guess - kGuessWindow, hi2 = guess + kGuessWindow;
-        if (lo2 < lo) lo2 = lo;
-        if (hi2 > hi) hi2 = hi;
-        // the tile boundaries stop hammering the same few top-level keys (all ~10^4 searches would
-        // otherwise hit the same 32 cache lines in their first round)
-        const int64_t span = hi2 - lo2;
-        int64_t m;
-        if (lane == 30) m = lo2 > lo ? lo2 - 1 : -1;                 // must be true: split >= lo2
-        else if (lane == 31) m = hi2 < hi ? hi2 : -2;                // must be false: split <= hi2
-        else m = lo2 + (span / 30) * lane + ((span % 30) * lane) / 30;
-        bool t;
-        if (m == -1) t = true;
-        else if (m == -2) t = false;
-        else if (m >= hi2 && lane < 30) t = false;                   // span == 0
-        else t = __ldg(p.a + m) <= __ldg(p.b + (d - 1 - m));
-        const unsigned bal = __ballot_sync(0xffffffffu, t);
-        if ((bal >> 30) == 1u) {                                     // bracket holds: lane 30 true, lane 31 false
-            const int c = __popc(bal & 0x3fffffffu);
-            const int64_t m_last_true = __shfl_sync(0xffffffffu, m, c > 0 ? c - 1 : 0);
-            const int64_t m_first_false = __shfl_sync(0xffffffffu, m, c < 30 ? c : 29);
-            lo = c > 0 ? m_last_true + 1 : lo2;
-            hi = c < 30 ? m_first_false : hi2;
+    // predicate "the split lies above m": a[m] <= b[d-1-m], defined for lo <= m < hi; true below the split
+    if (hi - lo > 64) {
+        // average key gaps of the two arrays (the same four L2-resident keys for every diagonal); single
+        // precision is plenty: the estimate only has to land within a few elements
+        const float span_a = (float)(__ldg(p.a + p.na - 1) - __ldg(p.a));
+        const float span_b = (float)(__ldg(p.b + p.nb - 1) - __ldg(p.b));
+        const float gap = __fdividef(span_a, (float)(p.na > 1 ? p.na - 1 : 1)) +
+                          __fdividef(span_b, (float)(p.nb > 1 ? p.nb - 1 : 1));
+        const float inv_gap = gap > 0.0f ? __fdividef(1.0f, gap) : 0.0f;
+        // proportional first guess (double keeps 2^53 positions exact enough; no 128-bit division)
+        int64_t g = (int64_t)((double)d * p.frac_a);
+        for (int it = 0; it < 3 && hi - lo > 64; ++it) {
+            g = g < lo ? lo : (g > hi - 1 ? hi - 1 : g);
+            const int64_t ka = __ldg(p.a + g), kb = __ldg(p.b + (d - 1 - g));          // uniform: one transaction each
+            if (ka <= kb) lo = g + 1;                                                // the split lies above g
+            else hi = g;
+            const int64_t mv = (int64_t)__float2ll_rn((float)(ka - kb) * inv_gap);
+            g -= mv;
+            if (mv > -12 && mv < 12) break;
+        }
+        // one window of 32 consecutive candidates around the estimate
+        if (hi - lo > 32) {
+            int64_t base = g - 16;
+            if (base > hi - 32) base = hi - 32;
+            if (base < lo) base = lo;
+            const int64_t m = base + lane;
+            const bool t = m < hi ? (__ldg(p.a + m) <= __ldg(p.b + (d - 1 - m))) : false;
+            const int c = __popc(__ballot_sync(0xffffffffu, t));
+            if (c > 0 && c < 32) return base + c;                // the crossing is inside the window
+            if (c == 0) hi = base;                               // everything here is past the split
+            else lo = base + 32 < hi ? base + 32 : hi;           // everything here is before it
         }
     }
     while (lo < hi) {
@@ -775,6 +787,7 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     PartitionParams pp{};
     pp.a = p.a; pp.b = p.b; pp.na = p.na; pp.nb = p.nb;
     pp.ntiles = ntiles;
+    pp.frac_a = (double)p.na / (double)total;
     pp.tile_items = kTile;
     pp.desc = reinterpret_cast<uint64_t*>(ws->payload);
     char* pay = reinterpret_cast<char*>(ws->payload);

@@ -4,10 +4,27 @@
 
 namespace spb {
 
+// Is this stream being captured into a CUDA graph?  Buffers cannot grow then (cudaMalloc / cudaFree /
+// cudaStreamSynchronize are illegal during capture): run the same call once before capturing.
+static bool capturing(cudaStream_t stream) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return st != cudaStreamCaptureStatusNone;
+}
+#define SPB_NO_GROWTH_IN_CAPTURE(stream) \
+    do {                                 \
+        if (capturing(stream)) return SPB_ERR_CAPTURE; \
+    } while (0)
+
 int workspace_reserve(spb_workspace* ws, size_t state_bytes, cudaStream_t stream) {
     if (!ws) return SPB_ERR_BAD_ARG;
     const size_t bytes = kWsMiscBytes + state_bytes;
+    ws->last_state_bytes = state_bytes;
     if (ws->bytes >= bytes && ws->dev) return SPB_OK;
+    SPB_NO_GROWTH_IN_CAPTURE(stream);
     size_t want = (bytes + state_bytes / 2 + (1u << 20) + 255) & ~(size_t)255;
     if (ws->dev) {
         SPB_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -27,6 +44,7 @@ int workspace_reserve(spb_workspace* ws, size_t state_bytes, cudaStream_t stream
 int workspace_reserve_payload(spb_workspace* ws, size_t bytes, cudaStream_t stream) {
     if (!ws) return SPB_ERR_BAD_ARG;
     if (ws->payload_bytes >= bytes && ws->payload) return SPB_OK;
+    SPB_NO_GROWTH_IN_CAPTURE(stream);
     if (ws->payload) {
         SPB_CUDA_TRY(cudaStreamSynchronize(stream));
         SPB_CUDA_TRY(cudaFree(ws->payload));
@@ -41,7 +59,9 @@ int workspace_reserve_payload(spb_workspace* ws, size_t bytes, cudaStream_t stre
 
 int workspace_reserve_state16(spb_workspace* ws, size_t bytes, cudaStream_t stream) {
     if (!ws) return SPB_ERR_BAD_ARG;
+    ws->last_state16_bytes = bytes;
     if (ws->state16_bytes >= bytes && ws->state16) return SPB_OK;
+    SPB_NO_GROWTH_IN_CAPTURE(stream);
     if (ws->state16) {
         SPB_CUDA_TRY(cudaStreamSynchronize(stream));
         SPB_CUDA_TRY(cudaFree(ws->state16));
@@ -58,6 +78,7 @@ int workspace_reserve_state16(spb_workspace* ws, size_t bytes, cudaStream_t stre
 int workspace_reserve_accum(spb_workspace* ws, size_t bytes, cudaStream_t stream) {
     if (!ws) return SPB_ERR_BAD_ARG;
     if (ws->accum_bytes >= bytes && ws->accum) return SPB_OK;
+    SPB_NO_GROWTH_IN_CAPTURE(stream);
     if (ws->accum) {
         SPB_CUDA_TRY(cudaStreamSynchronize(stream));
         SPB_CUDA_TRY(cudaFree(ws->accum));
@@ -68,11 +89,22 @@ int workspace_reserve_accum(spb_workspace* ws, size_t bytes, cudaStream_t stream
     SPB_CUDA_TRY(cudaMalloc(&ws->accum, want));
     SPB_CUDA_TRY(cudaMemsetAsync(ws->accum, 0, want, stream));     // zero from here on: users clean up after themselves
     ws->accum_bytes = want;
+    ws->accum_dirty = 0;
     return SPB_OK;
 }
 
-// next launch epoch (1 .. 2^14-1); re-zero the state words when the counter wraps
+// next launch epoch (1 .. 2^14-1); re-zero the state words when the counter wraps.
+// CUDA graphs: a captured launch carries its epoch as a baked-in kernel argument, so every replay would
+// meet the words of the previous replay tagged with the very same epoch.  While the stream is being
+// captured, the words the call asked for (workspace_reserve / _state16 just before) are therefore wiped by
+// a memset node in front of the launch: a replayed chain is self-contained.
 int workspace_next_epoch(spb_workspace* ws, cudaStream_t stream, uint32_t* epoch) {
+    if (capturing(stream)) {
+        if (ws->last_state_bytes)
+            SPB_CUDA_TRY(cudaMemsetAsync((char*)ws->dev + kWsMiscBytes, 0, ws->last_state_bytes, stream));
+        if (ws->state16 && ws->last_state16_bytes)
+            SPB_CUDA_TRY(cudaMemsetAsync(ws->state16, 0, ws->last_state16_bytes, stream));
+    }
     ws->epoch += 1;
     if (ws->epoch >= (1u << kEpochBits)) {
         SPB_CUDA_TRY(cudaMemsetAsync(ws->dev, 0, ws->bytes, stream));
@@ -114,6 +146,9 @@ int spb_workspace_create(spb_workspace** ws) {
     w->state16_bytes = 0;
     w->accum = nullptr;
     w->accum_bytes = 0;
+    w->accum_dirty = 0;
+    w->last_state_bytes = 0;
+    w->last_state16_bytes = 0;
     *ws = w;
     return SPB_OK;
 }

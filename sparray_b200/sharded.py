@@ -18,11 +18,15 @@ run on it unchanged.
     the fused merge kernels READ THE PARTNER'S SLICES OVER NVLINK inside their TMA staging -- the
     exchange and the merge are one kernel, nothing is repartitioned, no intermediate buffer exists;
     the only collective is one tiny all-gather of cut positions;
-  * axis sums: local segmented reduce; only output keys on a shard border can collide, so
-    the borders are fixed by an allgather of one (key, value) pair per rank -- or, when the
-    reduced axis is not the last one, an all-to-all of the partial sums by output-key range
-    followed by a local merge-reduce;
-  * transpose: re-key locally, all-to-all by new-key splitters, local sort;
+  * axis sums: a range shard can only touch the output rows of its own flat range, so every rank reduces
+    locally into a WINDOW of the reduced array (dense accumulators for that window only).  When the
+    splitters do not cut through a block of the reduced axis (``sampled_splitters(..., align=...)``)
+    that is the whole op: NO collective.  Otherwise the partial sums of the cut rows travel to the rank
+    that owns the row (one variable-size exchange) and are merged with the union-add kernel.  When every
+    rank touches every output cell (the leading axis is reduced) and the reduced array is small:
+    dense per-GPU accumulators + all-reduce;
+  * transpose: local re-key + sort (only the bits that matter), exchange of contiguous slices by new-key
+    splitters, then a pairwise merge of the received sorted runs (union kernel) -- no second sort;
   * SpMV: rows follow flat ranges (row-major), x is replicated, y partials are all-reduced.
 
 The kernels are reached through a small ``ops`` object so the orchestration (splitter
@@ -65,6 +69,15 @@ class CudaOps:
     def reduce_by_key(self, keys, vals, divisor=1):
         return self.k.reduce_by_key(keys, vals, divisor)
 
+    def sum_axis_window(self, idx, val, shape, axis, cell_lo, cell_hi, n_dev=None):
+        """Local sum(axis) of a shard whose output cells all lie in [cell_lo, cell_hi):
+        (sorted unique keys, float64 sums, device count or None)."""
+        return self.k.sum_axis(idx, val, shape, axis, n_dev=n_dev, window=(cell_lo, cell_hi))
+
+    def can_chain_count(self, cells):
+        """True when sum_axis_window on a window of `cells` cells takes the producer's count from the device."""
+        return 0 < cells <= self.k._l2_resident_cells(self.k._cur_dev())
+
     def rekey_sort(self, idx, val, in_s, out_s, div, bits):
         return self.k.rekey_sort(idx, val, in_s, out_s, div, bits)
 
@@ -101,10 +114,12 @@ def even_splitters(shape, world):
     return cuts + [size]
 
 
-def sampled_splitters(local_idx, shape, group=None, ops=None, samples_per_rank=256):
+def sampled_splitters(local_idx, shape, group=None, ops=None, samples_per_rank=256, align=1):
     """Splitters that balance nnz: every rank contributes evenly spaced samples of its sorted
     indices, the samples are all-gathered (a few KB), and the r/world quantiles become the
-    boundaries."""
+    boundaries.  align > 1 snaps every interior boundary down to a multiple
+    of `align` flat indices -- e.g. ``prod(shape[axis:])`` so that ``sum(axis)`` never cuts an
+    output row and needs no exchange."""
     world = dist.get_world_size(group)
     n = local_idx.numel()
     take = min(samples_per_rank, n)
@@ -123,17 +138,21 @@ def sampled_splitters(local_idx, shape, group=None, ops=None, samples_per_rank=2
     size = _size(shape)
     if len(allv) == 0:
         return even_splitters(shape, world)
-    cuts = [0] + [int(allv[len(allv) * r // world]) for r in range(1, world)] + [size]
+    align = max(int(align), 1)
+    cuts = [0] + [int(allv[len(allv) * r // world]) // align * align for r in range(1, world)] + [size]
     for r in range(1, world + 1):          # keep them monotone
         cuts[r] = max(cuts[r], cuts[r - 1])
     return cuts
 
 
 class ShardedFlatSparray:
-    """This rank's shard of a range-partitioned FlatSparray."""
+    """This rank's shard of a range-partitioned FlatSparray.  Like FlatSparray, results whose size
+    depends on the data are lazily counted: the worst-case-sized buffers and the device-side count
+    are kept until ``indices`` / ``data`` / ``nnz_local`` are looked at, so a chain such as
+    ``(a * b).sum(axis)`` on co-partitioned, row-aligned shards never waits for the host."""
 
-    def __init__(self, indices, data, shape, splitters, group=None, ops=None):
-        self.indices, self.data = indices, data
+    def __init__(self, indices, data, shape, splitters, group=None, ops=None, _pending=None):
+        self._indices, self._data, self._pending = indices, data, _pending
         self.shape = tuple(int(s) for s in shape)
         self.splitters = [int(s) for s in splitters]
         self.group = group
@@ -141,6 +160,23 @@ class ShardedFlatSparray:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         assert len(self.splitters) == self.world + 1
+
+    def _resolve(self):
+        idx, val, cnt = self._pending
+        n = int(cnt.item())
+        self._indices, self._data, self._pending = idx[:n], val[:n], None
+
+    @property
+    def indices(self):
+        if self._pending is not None:
+            self._resolve()
+        return self._indices
+
+    @property
+    def data(self):
+        if self._pending is not None:
+            self._resolve()
+        return self._data
 
     @property
     def nnz_local(self):
@@ -151,7 +187,10 @@ class ShardedFlatSparray:
         dist.all_reduce(t, group=self.group)
         return int(t.item())
 
-    def _like(self, indices, data, shape=None, splitters=None):
+    def _like(self, indices, data, shape=None, splitters=None, cnt=None):
+        if cnt is not None:
+            return ShardedFlatSparray(None, None, shape or self.shape, splitters or self.splitters, self.group,
+                                      self.ops, _pending=(indices, data, cnt))
         return ShardedFlatSparray(indices, data, shape or self.shape, splitters or self.splitters,
                                   self.group, self.ops)
 
@@ -160,6 +199,10 @@ class ShardedFlatSparray:
         assert self.shape == other.shape
         if other.splitters != self.splitters:
             other = other.repartition(self.splitters)       # the only communication of a binop
+        lazy = getattr(self.ops, "binop_lazy", None)
+        if lazy is not None:
+            idx, val, cnt = lazy(kind, op, self.indices, self.data, other.indices, other.data)
+            return self._like(idx, val, cnt=cnt)
         idx, val = self.ops.binop(kind, op, self.indices, self.data, other.indices, other.data)
         return self._like(idx, val)
 
@@ -229,102 +272,66 @@ class ShardedFlatSparray:
             out_v.append(v)
         return self._like(torch.cat(out_i), torch.cat(out_v))
 
-    # ---- repartition: counts allgather + one variable-size all-to-all --------------------------------
+    # ---- repartition: one count exchange + one variable-size exchange ----------------------------------
     def repartition(self, new_splitters):
         new_splitters = [int(s) for s in new_splitters]
-        dev = self.indices.device
-        # destination d receives my elements in [new[d], new[d+1]): a contiguous slice of my sorted shard
-        bounds = torch.tensor(new_splitters, dtype=torch.int64, device=dev)
-        cut = self.ops.lower_bound(self.indices, bounds).cpu().tolist()
-        send_counts = [cut[d + 1] - cut[d] for d in range(self.world)]
-        counts = torch.tensor(send_counts, dtype=torch.int64, device=dev)
-        all_counts = [torch.empty_like(counts) for _ in range(self.world)]
-        dist.all_gather(all_counts, counts, group=self.group)
-        recv_counts = torch.stack(all_counts)[:, self.rank].cpu().tolist()      # one read-back, not one per source
-        lo = cut[0]
-        send_idx = self.indices[lo:cut[-1]].contiguous()
-        send_val = self.data[lo:cut[-1]].contiguous()
-        recv_idx = torch.empty(sum(recv_counts), dtype=torch.int64, device=dev)
-        recv_val = torch.empty(sum(recv_counts), dtype=self.data.dtype, device=dev)
-        dist.all_to_all_single(recv_idx, send_idx, recv_counts, send_counts, group=self.group)
-        dist.all_to_all_single(recv_val, send_val, recv_counts, send_counts, group=self.group)
+        recv_idx, recv_val, _ = _exchange_runs(self.indices, self.data, new_splitters, self.group, self.ops)
         # sources are range-ordered, so the concatenation in source order is globally sorted
         return self._like(recv_idx, recv_val, splitters=new_splitters)
 
     # ---- reductions -------------------------------------------------------------------------------------
     def sum(self, axis):
         """sum over one axis -> ShardedFlatSparray with float64 data (flat.py:607-626)."""
-        from . import _plan
         axis = int(axis) % len(self.shape)
         new_shape = self.shape[:axis] + self.shape[axis + 1:]
-        plan = _plan.axis_sum_plan(self.shape, axis)
-        dev = self.indices.device
-        if plan[0] == "last":
-            div = plan[1]
-            keys, sums = self.ops.reduce_by_key(self.indices, self.data, div)
-            new_split = [s // div for s in self.splitters[:-1]] + [_size(new_shape)]
-            return self._fix_borders(keys, sums, new_shape, new_split)
-        _, in_s, out_s, bits = plan
-        cells = _size(new_shape)
-        if cells <= DENSE_ALLREDUCE_MAX_CELLS:
-            # reduced array small enough to hold densely on every GPU (SURVEY.md section 8e): local float64
-            # accumulators, one all-reduce of the sums and one of the "touched" flags, then every rank
-            # emits its own range of output cells (ranges aligned to 64 cells)
-            acc, touched = self.ops.axis_accumulate(self.indices, self.data, in_s, out_s, cells)
+        if not new_shape:
+            new_shape = (1,)
+        span = self.shape[axis]
+        inner = _size(self.shape[axis + 1:])             # cells of one output row
+        block = span * inner                             # flat indices that fold into one output row
+        cells_total = _size(self.shape) // max(span, 1)
+        sp = self.splitters
+        # output rows each rank's flat range can touch: [row_lo, row_hi]
+        rows = [(sp[r] // block, (sp[r + 1] - 1) // block) for r in range(self.world) if sp[r + 1] > sp[r]]
+        window_cells = sum((hi - lo + 1) * inner for lo, hi in rows)
+        if cells_total <= DENSE_ALLREDUCE_MAX_CELLS and window_cells >= 2 * cells_total:
+            # every rank touches (nearly) every output cell -- the leading axis is reduced -- and the reduced
+            # array is small enough to hold densely on every GPU (SURVEY.md section 8e): local float64
+            # accumulators, one all-reduce of the sums and one of the "touched" flags, then every rank emits
+            # its own range of output cells (ranges aligned to 64 cells)
+            from . import _plan
+            in_s, out_s = _plan.rekey_strides(self.shape, [a for a in range(len(self.shape)) if a != axis])
+            acc, touched = self.ops.axis_accumulate(self.indices, self.data, in_s, out_s, cells_total)
             dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
             dist.all_reduce(touched, op=dist.ReduceOp.MAX, group=self.group)
-            per = -(-cells // self.world)
+            per = -(-cells_total // self.world)
             per = -(-per // 64) * 64
-            out_split = [min(r * per, cells) for r in range(self.world)] + [cells]
+            out_split = [min(r * per, cells_total) for r in range(self.world)] + [cells_total]
             keys, sums = self.ops.emit_touched(acc, touched, out_split[self.rank], out_split[self.rank + 1])
             return ShardedFlatSparray(keys, sums, new_shape, out_split, self.group, self.ops)
-        # middle axis, large output: local re-key + sort + reduce, then exchange partial sums by output-key range
-        keys, vals = self.ops.rekey_sort(self.indices, self.data, in_s, out_s, 1, bits)
-        keys, sums = self.ops.reduce_by_key(keys, vals, 1)
-        out_split = even_splitters(new_shape, self.world)
-        part = ShardedFlatSparray(keys, sums, new_shape, [0] * self.world + [_size(new_shape)], self.group, self.ops)
-        part.splitters = None                                 # not range-partitioned yet
-        got = _exchange_unsorted(part, out_split)
-        # every source contributed a sorted run: sort by key again (bits of the output key) and reduce
-        kbits = max(_size(new_shape) - 1, 1).bit_length()
-        k2, v2 = self.ops.rekey_sort(got[0], got[1], [], [], 1, kbits)
-        k3, s3 = self.ops.reduce_by_key(k2, v2, 1)
-        return ShardedFlatSparray(k3, s3, new_shape, out_split, self.group, self.ops)
-
-    def _fix_borders(self, keys, sums, new_shape, new_split):
-        """After a last-axis reduction only the FIRST output key of a rank can also be the last
-        key of an earlier rank (a shard boundary inside a row).  Everybody all-gathers
-        (first key, last key, count, first sum); the earliest rank of each chain keeps the key
-        and absorbs the partial sums, the others drop their first element."""
-        dev = keys.device
-        n = keys.numel()
-        meta = torch.tensor([int(keys[0]) if n else -1, int(keys[-1]) if n else -1, n], dtype=torch.int64, device=dev)
-        info = torch.zeros(1, dtype=torch.float64, device=dev)
-        if n:
-            info[0] = sums[0]
-        metas = [torch.empty_like(meta) for _ in range(self.world)]
-        infos = [torch.empty_like(info) for _ in range(self.world)]
-        dist.all_gather(metas, meta, group=self.group)
-        dist.all_gather(infos, info, group=self.group)
-        firsts = [int(m[0]) for m in metas]
-        lasts = [int(m[1]) for m in metas]
-        counts = [int(m[2]) for m in metas]
-        dup = [False] * self.world
-        owner = list(range(self.world))
-        prev = None
-        for r in range(self.world):
-            if counts[r] == 0:
-                continue
-            if prev is not None and lasts[prev] == firsts[r]:
-                dup[r] = True
-                owner[r] = owner[prev] if (counts[prev] == 1 and dup[prev]) else prev
-            prev = r
-        sums = sums.clone()
-        if dup[self.rank]:
-            keys, sums = keys[1:], sums[1:]
-        for r in range(self.rank + 1, self.world):
-            if dup[r] and owner[r] == self.rank:
-                sums[-1] += infos[r][0].to(sums.device)
+        # local reduction into the window of output rows my flat range touches
+        lo, hi = sp[self.rank], sp[self.rank + 1]
+        row_lo = lo // block
+        row_hi = (hi - 1) // block if hi > lo else row_lo - 1
+        cell_lo, cell_hi = row_lo * inner, (row_hi + 1) * inner
+        if self._pending is not None and self.ops.can_chain_count(cell_hi - cell_lo):
+            p_idx, p_val, p_cnt = self._pending          # the producer's count never leaves the device
+            keys, sums, cnt = self.ops.sum_axis_window(p_idx, p_val, self.shape, axis, cell_lo, cell_hi, n_dev=p_cnt)
+        else:
+            keys, sums, cnt = self.ops.sum_axis_window(self.indices, self.data, self.shape, axis, cell_lo, cell_hi)
+        # an output row cut by a splitter belongs to the rank on the right of the cut
+        new_split = [(s // block) * inner for s in sp[:-1]] + [cells_total]
+        if all(s % block == 0 for s in sp[1:-1]):
+            return ShardedFlatSparray(keys, sums, new_shape, new_split, self.group, self.ops,
+                                      _pending=None) if cnt is None else \
+                ShardedFlatSparray(None, None, new_shape, new_split, self.group, self.ops, _pending=(keys, sums, cnt))
+        if cnt is not None:
+            n = int(cnt.item())
+            keys, sums = keys[:n], sums[:n]
+        # the partial sums of cut rows go to the row's owner: every destination receives sorted runs that
+        # can only overlap inside its first row; merge them with the union-add kernel
+        recv_idx, recv_val, counts = _exchange_runs(keys, sums, new_split, self.group, self.ops)
+        keys, sums = _merge_runs(self.ops, recv_idx, recv_val, counts, "add")
         return ShardedFlatSparray(keys, sums, new_shape, new_split, self.group, self.ops)
 
     # ---- SpMV --------------------------------------------------------------------------------------------
@@ -339,17 +346,17 @@ class ShardedFlatSparray:
 
     # ---- transpose ---------------------------------------------------------------------------------------
     def transpose(self, *axes):
+        """Local re-key + sort of the bits that matter, exchange of contiguous slices by new-key range,
+        pairwise merge of the received sorted runs (their keys are disjoint) -- no second sort."""
         from . import _plan
         ndim = len(self.shape)
         axes = tuple(range(ndim - 1, -1, -1)) if not axes else tuple(int(a) for a in axes)
         new_shape = tuple(self.shape[a] for a in axes)
-        in_s, out_s, _, _ = _plan.transpose_plan(self.shape, axes)
-        keys, vals = self.ops.rekey_sort(self.indices, self.data, in_s, out_s, 1, 0)     # re-key only
+        in_s, out_s, div, bits = _plan.transpose_plan(self.shape, axes)
+        keys, vals = self.ops.rekey_sort(self.indices, self.data, in_s, out_s, div, bits)
         out_split = even_splitters(new_shape, self.world)
-        part = ShardedFlatSparray(keys, vals, new_shape, [0] * (self.world + 1), self.group, self.ops)
-        got = _exchange_unsorted(part, out_split)
-        kbits = max(_size(new_shape) - 1, 1).bit_length()
-        k2, v2 = self.ops.rekey_sort(got[0], got[1], [], [], 1, kbits)
+        recv_idx, recv_val, counts = _exchange_runs(keys, vals, out_split, self.group, self.ops)
+        k2, v2 = _merge_runs(self.ops, recv_idx, recv_val, counts, "override")
         return ShardedFlatSparray(k2, v2, new_shape, out_split, self.group, self.ops)
 
     # ---- gather to one canonical array (tests / small results) --------------------------------------------
@@ -371,6 +378,73 @@ class ShardedFlatSparray:
         idx = np.concatenate([gi[r][:ns[r]].cpu().numpy() for r in range(self.world)])
         val = np.concatenate([gv[r][:ns[r]].cpu().numpy() for r in range(self.world)])
         return idx, val
+
+
+def _exchange_runs(keys, vals, splitters, group, ops):
+    """Variable-size exchange of a SORTED local (keys, vals) array by destination key range: destination d
+    gets my elements in [splitters[d], splitters[d + 1]) -- a contiguous slice, found by a batched binary
+    search.  One small device-side all-gather of the cut positions, ONE host read-back (of the gathered
+    matrix, which holds my own cuts too), then the index and the value slices of all peers travel in one
+    batch of point-to-point operations (a single NCCL group).
+    Returns (received keys, received values, per-source counts); the received array is the concatenation
+    of one sorted run per source, in source order."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = keys.device
+    bounds = torch.tensor([int(s) for s in splitters], dtype=torch.int64, device=dev)
+    cut = ops.lower_bound(keys, bounds).contiguous()                              # [world + 1]
+    all_cut = torch.empty(world * (world + 1), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_cut, cut, group=group)
+    cuts = all_cut.cpu().reshape(world, world + 1).tolist()                         # the one read-back
+    mine = cuts[rank]
+    recv_counts = [cuts[s][rank + 1] - cuts[s][rank] for s in range(world)]
+    total = sum(recv_counts)
+    recv_idx = torch.empty(total, dtype=torch.int64, device=dev)
+    recv_val = torch.empty(total, dtype=vals.dtype, device=dev)
+    offs = [0]
+    for c in recv_counts:
+        offs.append(offs[-1] + c)
+    # my own slice never leaves the GPU
+    if recv_counts[rank]:
+        recv_idx[offs[rank]:offs[rank + 1]].copy_(keys[mine[rank]:mine[rank + 1]])
+        recv_val[offs[rank]:offs[rank + 1]].copy_(vals[mine[rank]:mine[rank + 1]])
+    p2p = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        g_peer = peer if group is None else dist.get_global_rank(group, peer)
+        if mine[peer + 1] > mine[peer]:
+            p2p.append(dist.P2POp(dist.isend, keys[mine[peer]:mine[peer + 1]], g_peer, group))
+            p2p.append(dist.P2POp(dist.isend, vals[mine[peer]:mine[peer + 1]], g_peer, group))
+        if recv_counts[peer]:
+            p2p.append(dist.P2POp(dist.irecv, recv_idx[offs[peer]:offs[peer + 1]], g_peer, group))
+            p2p.append(dist.P2POp(dist.irecv, recv_val[offs[peer]:offs[peer + 1]], g_peer, group))
+    if p2p:
+        for req in dist.batch_isend_irecv(p2p):
+            req.wait()
+    return recv_idx, recv_val, recv_counts
+
+
+def _merge_runs(ops, keys, vals, counts, op):
+    """Merge the sorted runs of a received array (counts per source, in order) into one sorted,
+    duplicate-free array with the union kernel: op 'add' sums values of keys present in several runs
+    (partial sums of a cut row), 'override' is for runs whose keys are disjoint (transpose).  Pairwise
+    tree: log2(#runs) rounds."""
+    runs, off = [], 0
+    for c in counts:
+        if c:
+            runs.append((keys[off:off + c], vals[off:off + c]))
+        off += c
+    if not runs:
+        return keys[:0], vals[:0]
+    while len(runs) > 1:
+        nxt = []
+        for i in range(0, len(runs) - 1, 2):
+            nxt.append(ops.binop("union", op, runs[i][0], runs[i][1], runs[i + 1][0], runs[i + 1][1]))
+        if len(runs) % 2:
+            nxt.append(runs[-1])
+        runs = nxt
+    return runs[0]
 
 
 class PeerShards:
@@ -415,34 +489,6 @@ class PeerShards:
             return self._idx[c0:c0 + n], self._val[c0:c0 + n]
         return (self._h_idx.get_buffer(src, (n,), torch.int64, storage_offset=int(c0)),
                 self._h_val.get_buffer(src, (n,), self.dtype, storage_offset=int(c0)))
-
-
-def _exchange_unsorted(part, out_split):
-    """All-to-all of (key, value) pairs whose keys are NOT range-partitioned by source (after a
-    re-key): the pairs are bucketed by destination with one stable sort pass on the
-    destination id, exchanged, and returned unsorted (the caller sorts locally)."""
-    ops, group = part.ops, part.group
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    keys, vals = part.indices, part.data
-    dev = keys.device
-    bounds = torch.tensor(out_split[1:-1], dtype=torch.int64, device=dev)
-    # destination of every pair = number of boundaries <= key: keys are sorted locally after the
-    # caller's reduce / (for transpose) not sorted -- so sort them first by the full key
-    kbits = max(int(out_split[-1]) - 1, 1).bit_length()
-    keys, vals = ops.rekey_sort(keys, vals, [], [], 1, kbits)
-    full = torch.tensor(out_split, dtype=torch.int64, device=dev)
-    cut = ops.lower_bound(keys, full).cpu().tolist()
-    send_counts = [cut[d + 1] - cut[d] for d in range(world)]
-    counts = torch.tensor(send_counts, dtype=torch.int64, device=dev)
-    all_counts = [torch.empty_like(counts) for _ in range(world)]
-    dist.all_gather(all_counts, counts, group=group)
-    recv_counts = [int(all_counts[s][rank].item()) for s in range(world)]
-    recv_idx = torch.empty(sum(recv_counts), dtype=torch.int64, device=dev)
-    recv_val = torch.empty(sum(recv_counts), dtype=vals.dtype, device=dev)
-    dist.all_to_all_single(recv_idx, keys.contiguous(), recv_counts, send_counts, group=group)
-    dist.all_to_all_single(recv_val, vals.contiguous(), recv_counts, send_counts, group=group)
-    return recv_idx, recv_val
 
 
 def scatter_from_full(indices, data, shape, splitters=None, group=None, ops=None, device=None):

@@ -60,7 +60,23 @@ def main():
         same(X.binop_peer(Bp, "union", "sub"), fo.pairwise_union(ai, av, bi, -bv, np.add))
     Bp.barrier()
     for axis in range(4):
-        same(A2.sum(axis), fo.sum_axis(ai, av, shape, axis)[:2], exact=False)
+        S = A2.sum(axis)
+        same(S, fo.sum_axis(ai, av, shape, axis)[:2], exact=False)
+        sk = S.indices
+        assert bool(((sk >= S.splitters[rank]) & (sk < S.splitters[rank + 1])).all().item()), "sum() result breaks its splitters"
+    # the bench chain on co-partitioned, block-aligned shards: no collective, no host wait until the end
+    for axis in (2, 3, 1):
+        block = int(np.prod(shape[axis:]))
+        spa = sh.sampled_splitters(A.indices, shape, align=block)
+        A3, B3 = A.repartition(spa), B.repartition(spa)
+        C = A3 * B3
+        S = C.sum(axis)
+        ci, cv = fo.pairwise_intersect(ai, av, bi, bv, np.multiply)
+        same(S, fo.sum_axis(ci, cv, shape, axis)[:2], exact=False)
+        same(C, (ci, cv))
+        U = A3 + B3
+        ui, uv = fo.pairwise_union(ai, av, bi, bv, np.add)
+        same(U.sum(axis), fo.sum_axis(ui, uv, shape, axis)[:2], exact=False)
     for axes in ((3, 2, 1, 0), (2, 0, 3, 1)):
         same(A2.transpose(*axes), fo.transpose(ai, av, shape, axes)[:2])
     x = rng.standard_normal(shape[-1]).astype(np.float32)

@@ -515,3 +515,52 @@ def test_lazily_counted_chain_every_axis(sp):
     C = A * B
     assert_sparse_same(C, (ci, cv, shape))
     assert C._pending is None and C.nnz == len(ci)
+
+
+def test_cuda_graph_capture_of_a_chain(sp):
+    """The whole chain c = a*b; c.sum(axis) -- and a union, whose look-back words carry launch epochs -- captured
+    into a CUDA graph and replayed: every replay must give the eager result, also after the operands'
+    values changed in place and after other (eager) calls ran in between."""
+    import torch
+    rng = np.random.default_rng(31)
+    shape = (64, 64, 48, 16)
+    ai, av = rand_operand(rng, shape, 400_000, np.float32)
+    bi, bv = rand_operand(rng, shape, 380_000, np.float32)
+    A = sp.FlatSparray(ai, av, shape=shape, is_canonical=True)
+    B = sp.FlatSparray(bi, bv, shape=shape, is_canonical=True)
+
+    def chain():
+        c = A * B
+        return c, c.sum(axis=2), A + B
+
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(3):                       # eager warm-up on the capture stream: scratch gets its size
+            chain()
+    side.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        c, s, u = chain()
+    for trial in range(3):
+        if trial == 1:                           # new values, same pattern: replays must pick them up
+            av = rng.standard_normal(len(ai)).astype(np.float32)
+            A.data.copy_(torch.from_numpy(av).cuda())
+        if trial == 2:                           # eager calls in between advance the epoch counter
+            with torch.cuda.stream(side):
+                for _ in range(5):
+                    (A + B).nnz
+            side.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
+        oa = fo.OracleSparray(ai, av, shape=shape, is_canonical=True)
+        ob = fo.OracleSparray(bi, bv, shape=shape, is_canonical=True)
+        oc = oa * ob
+        # pending results: read the device-side counts the replay produced
+        for got, want, exact in ((c, oc, True), (s, oc.sum(axis=2), False), (u, oa + ob, True)):
+            idx, val, cnt = got._pending
+            n = int(cnt.item())
+            np.testing.assert_array_equal(idx[:n].cpu().numpy(), want.indices)
+            if exact:
+                np.testing.assert_array_equal(val[:n].cpu().numpy(), want.data)
+            else:
+                np.testing.assert_allclose(val[:n].cpu().numpy(), want.data, rtol=1e-5, atol=1e-5)

@@ -31,7 +31,9 @@ class OracleOps:
         return torch.from_numpy(np.searchsorted(sorted_idx.numpy(), query.numpy(), side="left").astype(np.int64))
 
     def binop(self, kind, op, a_idx, a_val, b_idx, b_val):
-        uf = {"add": np.add, "sub": np.subtract, "mul": np.multiply, "minimum": np.minimum, "maximum": np.maximum}[op]
+        # "override" is only used on runs with disjoint keys, where any op that keeps x for (x, 0) will do
+        uf = {"add": np.add, "sub": np.subtract, "mul": np.multiply, "minimum": np.minimum, "maximum": np.maximum,
+              "override": np.add}[op]
         ai, av, bi, bv = a_idx.numpy(), a_val.numpy(), b_idx.numpy(), b_val.numpy()
         if kind == "union":
             if op == "sub":
@@ -48,6 +50,15 @@ class OracleOps:
             return torch.zeros(0, dtype=torch.int64), torch.zeros(0, dtype=torch.float64)
         u, inv = np.unique(k, return_inverse=True)
         return torch.from_numpy(u), torch.from_numpy(np.bincount(inv, vals.numpy().astype(np.float64), minlength=len(u)))
+
+    def sum_axis_window(self, idx, val, shape, axis, cell_lo, cell_hi, n_dev=None):
+        assert n_dev is None
+        i, v, _ = self.fo.sum_axis(idx.numpy(), val.numpy(), shape, axis)
+        assert len(i) == 0 or (i[0] >= cell_lo and i[-1] < cell_hi), "output outside the shard's window"
+        return torch.from_numpy(i), torch.from_numpy(v), None
+
+    def can_chain_count(self, cells):
+        return False
 
     def rekey_sort(self, idx, val, in_s, out_s, div, bits):
         k = idx.numpy().copy()
@@ -139,6 +150,24 @@ def _worker(rank, world, port, results):
                     assert S.shape == tuple(wshape)
                     assert np.array_equal(gi, wi), (axis, gi[:10], wi[:10])
                     np.testing.assert_allclose(gv, wv, rtol=1e-12, atol=1e-12)
+                    # the result obeys the splitters it advertises (round-1 review): every local key lies in
+                    # this rank's range, so a co-partitioned binop on two such results is purely local
+                    sk = S.indices.numpy()
+                    assert np.all((sk >= S.splitters[rank]) & (sk < S.splitters[rank + 1])), (axis, S.splitters)
+                    gi2, gv2 = (S + S).gather()
+                    assert np.array_equal(gi2, wi)
+                    np.testing.assert_allclose(gv2, 2 * wv, rtol=1e-12, atol=1e-12)
+        # splitters snapped to whole blocks of the reduced axis: the sum needs no exchange at all
+        for axis in (2, 1):
+            block = int(np.prod(shape[axis:]))
+            spa = sh.sampled_splitters(A.indices, shape, ops=ops, align=block)
+            assert all(x % block == 0 for x in spa[1:-1])
+            A3 = A.repartition(spa)
+            S = A3.sum(axis)
+            wi, wv, _ = fo.sum_axis(ai, av, shape, axis)
+            gi, gv = S.gather()
+            assert np.array_equal(gi, wi)
+            np.testing.assert_allclose(gv, wv, rtol=1e-12, atol=1e-12)
 
         # transpose: re-key, exchange by new-key range, local sort
         for axes in ((2, 1, 0), (1, 0, 2), (0, 2, 1)):
