@@ -200,6 +200,22 @@ int spb_reduce_by_key(int dtype, const int64_t* keys, const void* vals, int64_t 
 int spb_spmv(int dtype, const int64_t* idx, const void* vals, int64_t n, int64_t ncols, int64_t nrows,
              const void* x, double* y, spb_workspace* ws, spb_stream_t stream);
 
+/* Sparse x sparse matrix product C = A (m x k) . B (k x n) on sorted flat indices -- the
+ * reshape -> COO -> scipy CSR matmul -> from_spmatrix detour of flat.py:545-561 -- as expand / sort /
+ * compress.  b_row_ptr[j] = lower bound of j * n in B's indices (k + 1 entries, spb_lower_bound).
+ *   spb_spgemm_rowlen      len[e] = number of stored elements in row (a_idx[e] % k) of B
+ *   spb_exclusive_scan_i64 out[e] = len[0] + ... + len[e-1]; *total (device int64) = the sum
+ *   spb_spgemm_expand      one (i * n + c, a * b) pair per product, in A order; nprod = *total
+ * The pairs are then made canonical with spb_rekey_sort + spb_reduce_by_key like any unsorted
+ * constructor input (flat.py:32-35: duplicates are summed in float64). */
+int spb_spgemm_rowlen(const int64_t* a_idx, int64_t na, int64_t k, const int64_t* b_row_ptr, int64_t* len,
+                      spb_stream_t stream);
+int spb_exclusive_scan_i64(const int64_t* in, int64_t n, int64_t* out, int64_t* total, spb_workspace* ws,
+                           spb_stream_t stream);
+int spb_spgemm_expand(int dtype, const int64_t* a_idx, const void* a_val, int64_t na, int64_t k,
+                      const int64_t* offsets, const int64_t* b_row_ptr, const int64_t* b_idx, const void* b_val,
+                      int64_t n, int64_t nprod, int64_t* out_idx, void* out_val, spb_stream_t stream);
+
 /* ---- 5. re-key + stable radix sort: flat.py:32-35, 97-112, 617-620 ----------- */
 
 /* new_key = sum_g coord_g(idx) * out_strides[g], where coord_g unravels idx by

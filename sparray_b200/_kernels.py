@@ -253,6 +253,34 @@ def spmv(idx, val, ncols, nrows, x, vdtype):
     return y if vdtype == torch.float64 else cast(y, vdtype)
 
 
+def spgemm(a_idx, a_val, m, k, b_idx, b_val, n):
+    """C = A (m x k) . B (k x n) on sorted flat indices -> canonical (indices, values) of C (m x n):
+    expand / sort / compress, the O(products) form of flat.py:545-561.  Values share one dtype."""
+    require_cuda()
+    assert a_val.dtype == b_val.dtype
+    dev = a_idx.device
+    na = a_idx.numel()
+    empty = (torch.empty(0, dtype=torch.int64, device=dev), torch.empty(0, dtype=a_val.dtype, device=dev))
+    if na == 0 or b_idx.numel() == 0:
+        return empty
+    # rows of B are contiguous runs of its sorted flat indices (the queries j * n are index plumbing)
+    queries = torch.arange(int(k) + 1, device=dev, dtype=torch.int64) * int(n)
+    row_ptr, _ = lower_bound(b_idx, queries, want_found=False)
+    lens = torch.empty(na, dtype=torch.int64, device=dev)
+    check(lib.spb_spgemm_rowlen(ptr(a_idx), na, int(k), ptr(row_ptr), ptr(lens), stream()))
+    offs = torch.empty(na, dtype=torch.int64, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    check(lib.spb_exclusive_scan_i64(ptr(lens), na, ptr(offs), ptr(total), workspace(), stream()))
+    nprod = _count(total)
+    if nprod == 0:
+        return empty
+    p_idx = torch.empty(nprod, dtype=torch.int64, device=dev)
+    p_val = torch.empty(nprod, dtype=a_val.dtype, device=dev)
+    check(lib.spb_spgemm_expand(dt.spb_dtype(a_val.dtype), ptr(a_idx), ptr(a_val), na, int(k), ptr(offs), ptr(row_ptr),
+                                ptr(b_idx), ptr(b_val), int(n), nprod, ptr(p_idx), ptr(p_val), stream()))
+    return canonicalize(p_idx, p_val, max_key=int(m) * int(n) - 1)
+
+
 # ---- section 5: re-key + radix sort ------------------------------------------------------------
 
 def rekey_sort(idx, val, in_strides, out_strides, sort_divisor, sort_bits):

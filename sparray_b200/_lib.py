@@ -79,6 +79,9 @@ PROTOTYPES = {
     "spb_getitem_box": (c_int, [c_int, c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "spb_outer_sum": (c_int, [c_p, c_int, c_p, c_p, c_i64, c_p]),
     "spb_lookup_compact": (c_int, [c_int, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_p]),
+    "spb_spgemm_rowlen": (c_int, [c_p, c_i64, c_i64, c_p, c_p, c_p]),
+    "spb_exclusive_scan_i64": (c_int, [c_p, c_i64, c_p, c_p, c_p, c_p]),
+    "spb_spgemm_expand": (c_int, [c_int, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p]),
     "spb_rekey_sort": (c_int, [c_int, c_p, c_p, c_i64, c_int, c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p, c_p, c_p]),
 }
 

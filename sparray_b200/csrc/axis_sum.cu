@@ -30,9 +30,14 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
                                                               int64_t n, const int64_t* __restrict__ n_dev,
                                                               const Rekey rk, double* __restrict__ acc,
                                                               uint8_t* __restrict__ touched, const int64_t cell_lo,
-                                                              const int64_t cells) {
+                                                              const int64_t cells, uint64_t* __restrict__ clear_state,
+                                                              const int64_t clear_n) {
     cudaTriggerProgrammaticLaunchCompletion();
     cudaGridDependencySynchronize();   // operands (and n_dev) may come from the previous launch
+    // the look-back words of the emitting pass that follows start from zero (it waits for this whole grid):
+    // no memset node in front of it when the chain is captured into a CUDA graph
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < clear_n; i += (int64_t)gridDim.x * blockDim.x)
+        clear_state[i] = 0;
     if (n_dev) {                       // the producer's count never left the device; n is its upper bound
         const int64_t m = *n_dev;
         n = m < n ? m : n;
@@ -75,10 +80,12 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
             const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || kprev != key[u]);
             const int start = 31 - __clz(heads & ((2u << lane) - 1u));       // first lane of my run
             double s = v[u];
+            if (heads != 0xffffffffu) {                                       // some run is longer than one lane
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double up = __shfl_up_sync(0xffffffffu, s, o);
-                if (lane - o >= start) s += up;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double up = __shfl_up_sync(0xffffffffu, s, o);
+                    if (lane - o >= start) s += up;
+                }
             }
             const bool last = lane == 31 || ((heads >> (lane + 1)) & 1u);
             if (key[u] >= 0 && last) {
@@ -118,9 +125,14 @@ __global__ void __launch_bounds__(256) axis_accumulate_runs_kernel(const int64_t
                                                               int64_t n, const int64_t* __restrict__ n_dev,
                                                               const Rekey rk, double* __restrict__ acc,
                                                               uint8_t* __restrict__ touched, const int64_t cell_lo,
-                                                              const int64_t cells) {
+                                                              const int64_t cells, uint64_t* __restrict__ clear_state,
+                                                              const int64_t clear_n) {
     cudaTriggerProgrammaticLaunchCompletion();
     cudaGridDependencySynchronize();   // operands (and n_dev) may come from the previous launch
+    // the look-back words of the emitting pass that follows start from zero (it waits for this whole grid):
+    // no memset node in front of it when the chain is captured into a CUDA graph
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < clear_n; i += (int64_t)gridDim.x * blockDim.x)
+        clear_state[i] = 0;
     if (n_dev) {                       // the producer's count never left the device; n is its upper bound
         const int64_t m = *n_dev;
         n = m < n ? m : n;
@@ -245,7 +257,7 @@ namespace spb {
 
 static int launch_accumulate(int dtype, const int64_t* idx, const void* val, int64_t n, const int64_t* n_dev,
                              const Rekey& rk, int64_t cell_lo, int64_t cells, double* acc, uint8_t* touched,
-                             cudaStream_t stream) {
+                             uint64_t* clear_state, int64_t clear_n, cudaStream_t stream) {
     int64_t blocks = ceil_div(n, 256 * kAccUnroll);
     if (blocks > (int64_t)device_sm_count() * 16) blocks = (int64_t)device_sm_count() * 16;
     // long contiguous runs (innermost axis reduced, >= 8 elements per output cell on average): the variant
@@ -254,10 +266,10 @@ static int launch_accumulate(int dtype, const int64_t* idx, const void* val, int
 #define SPB_ACC(T)                                                                                            \
     if (long_runs) {                                                                                          \
         SPB_CUDA_TRY(launch_pdl(axis_accumulate_runs_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, \
-                                idx, (const T*)val, n, n_dev, rk, acc, touched, cell_lo, cells));             \
+                                idx, (const T*)val, n, n_dev, rk, acc, touched, cell_lo, cells, clear_state, clear_n)); \
     } else {                                                                                                  \
         SPB_CUDA_TRY(launch_pdl(axis_accumulate_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, idx, \
-                                (const T*)val, n, n_dev, rk, acc, touched, cell_lo, cells));                  \
+                                (const T*)val, n, n_dev, rk, acc, touched, cell_lo, cells, clear_state, clear_n)); \
     }                                                                                                         \
     break
     switch (dtype) {
@@ -276,14 +288,18 @@ static int launch_accumulate(int dtype, const int64_t* idx, const void* val, int
 }
 
 // cells of [0, cells) relative to acc / touched (touched readable up to the next multiple of 64)
+static int64_t select_tiles(int64_t cells) { return ceil_div(cells, 256 * kSelCells); }
+
+// precleared: the producer launch wiped the look-back words of this one (see the accumulate kernels)
 static int launch_select(double* acc, uint8_t* touched, int64_t cells, int64_t key_base, int64_t* out_idx,
-                         double* out_sums, int64_t* out_count, spb_workspace* ws, cudaStream_t stream) {
-    const int64_t ntiles = ceil_div(cells, 256 * kSelCells);
+                         double* out_sums, int64_t* out_count, spb_workspace* ws, cudaStream_t stream,
+                         bool precleared = false) {
+    const int64_t ntiles = select_tiles(cells);
     if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
     int rc = workspace_reserve(ws, (size_t)ntiles * 8, stream);
     if (rc) return rc;
     uint32_t epoch;
-    rc = workspace_next_epoch(ws, stream, &epoch);
+    rc = workspace_next_epoch(ws, stream, &epoch, !precleared);
     if (rc) return rc;
     SPB_CUDA_TRY(launch_pdl(select_touched_kernel, dim3((unsigned)ntiles), dim3(256), 0, stream, acc, touched, cells,
                             key_base, out_idx, out_sums, out_count, ws_state(ws), epoch));
@@ -321,9 +337,13 @@ static int axis_sum_window(int dtype, const int64_t* idx, const void* val, int64
     double* const acc = reinterpret_cast<double*>(ws->accum);
     uint8_t* const touched = reinterpret_cast<uint8_t*>(ws->accum) + acc_bytes;
     ws->accum_dirty = 1;
-    rc = launch_accumulate(dtype, idx, val, n, n_dev, rk, cell_lo, cells, acc, touched, stream);
+    const int64_t ntiles = select_tiles(cells);
+    if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
+    rc = workspace_reserve(ws, (size_t)ntiles * 8, stream);      // the emitting pass's look-back words, wiped by the
+    if (rc) return rc;                                           // accumulate launch
+    rc = launch_accumulate(dtype, idx, val, n, n_dev, rk, cell_lo, cells, acc, touched, ws_state(ws), ntiles, stream);
     if (rc) return rc;
-    rc = launch_select(acc, touched, cells, cell_lo, out_idx, out_sums, out_count, ws, stream);
+    rc = launch_select(acc, touched, cells, cell_lo, out_idx, out_sums, out_count, ws, stream, true);
     if (rc == SPB_OK) ws->accum_dirty = 0;
     return rc;
 }
@@ -358,7 +378,7 @@ extern "C" int spb_axis_accumulate(int dtype, const int64_t* idx, const void* va
     if (rc) return rc;
     if (n == 0 || cells == 0) return SPB_OK;
     if (!idx || !val || !acc || !touched) return SPB_ERR_BAD_ARG;
-    return launch_accumulate(dtype, idx, val, n, nullptr, rk, 0, cells, acc, touched, stream);
+    return launch_accumulate(dtype, idx, val, n, nullptr, rk, 0, cells, acc, touched, nullptr, 0, stream);
 }
 
 // Emit the touched cells of [cell_lo, cell_hi) in key order (keys are absolute cell numbers).

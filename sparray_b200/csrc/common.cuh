@@ -69,7 +69,7 @@ constexpr size_t kWsMiscBytes = 1u << 20;
 // (the kernel that consumes one puts it back to zero), so they need no memset per call either.
 constexpr size_t kWsCounterBytes = 256;
 int workspace_reserve(spb_workspace* ws, size_t state_bytes, cudaStream_t stream);   // workspace.cu
-int workspace_next_epoch(spb_workspace* ws, cudaStream_t stream, uint32_t* epoch);
+int workspace_next_epoch(spb_workspace* ws, cudaStream_t stream, uint32_t* epoch, bool wipe_in_capture = true);
 int workspace_reserve_payload(spb_workspace* ws, size_t bytes, cudaStream_t stream);
 int workspace_reserve_state16(spb_workspace* ws, size_t bytes, cudaStream_t stream);
 int workspace_reserve_accum(spb_workspace* ws, size_t bytes, cudaStream_t stream);

@@ -426,7 +426,7 @@ constexpr int kSpmvUnroll = 4;
 template <typename T>
 __global__ void __launch_bounds__(256) spmv_rows_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
                                                         int64_t n, const FastDiv div, const T* __restrict__ x,
-                                                        double* __restrict__ y) {
+                                                        double* __restrict__ y, const int64_t nrows) {
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -465,19 +465,20 @@ __global__ void __launch_bounds__(256) spmv_rows_kernel(const int64_t* __restric
                 if (lane - o >= start) s += up;
             }
             const bool last = lane == 31 || ((heads >> (lane + 1)) & 1u);
-            if (row[u] >= 0 && last) atomicAdd(y + row[u], s);
+            // rows beyond the shape (resize() allows stored indices past prod(shape)) must not touch y
+            if (row[u] >= 0 && row[u] < nrows && last) atomicAdd(y + row[u], s);
         }
     }
 }
 
 template <typename T>
-int launch_spmv_rows(const int64_t* idx, const void* vals, int64_t n, int64_t ncols, const void* x, double* y,
-                     cudaStream_t stream) {
+int launch_spmv_rows(const int64_t* idx, const void* vals, int64_t n, int64_t ncols, int64_t nrows, const void* x,
+                     double* y, cudaStream_t stream) {
     int64_t blocks = ceil_div(n, 256 * kSpmvUnroll);
     const int64_t cap = (int64_t)device_sm_count() * 16;
     if (blocks > cap) blocks = cap;
     spmv_rows_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(idx, (const T*)vals, n, make_fastdiv((uint64_t)ncols),
-                                                             (const T*)x, y);
+                                                             (const T*)x, y, nrows);
     SPB_LAUNCHED(1);
     return (int)cudaGetLastError();
 }
@@ -496,8 +497,8 @@ int spb_spmv(int dtype, const int64_t* idx, const void* vals, int64_t n, int64_t
     if (!idx || !vals || !x) return SPB_ERR_BAD_ARG;
     (void)ws;
     switch (dtype) {
-        case SPB_F32: return launch_spmv_rows<float>(idx, vals, n, ncols, x, y, stream);
-        case SPB_F64: return launch_spmv_rows<double>(idx, vals, n, ncols, x, y, stream);
+        case SPB_F32: return launch_spmv_rows<float>(idx, vals, n, ncols, nrows, x, y, stream);
+        case SPB_F64: return launch_spmv_rows<double>(idx, vals, n, ncols, nrows, x, y, stream);
         default: return SPB_ERR_UNSUPPORTED;
     }
 }

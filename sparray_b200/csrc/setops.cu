@@ -773,7 +773,7 @@ int launch_setop(SetopParams& p, spb_workspace* ws, cudaStream_t stream) {
     size_t payload_bytes = KIND == KIND_INTERSECT ? off_tbpos + (SEAM ? cap * 8 : 0) : off_slot;
     rc = workspace_reserve_payload(ws, payload_bytes, stream);
     if (rc) return rc;
-    rc = workspace_next_epoch(ws, stream, &p.epoch);
+    rc = workspace_next_epoch(ws, stream, &p.epoch, KIND == KIND_UNION);   // intersections use no look-back words
     if (rc) return rc;
     p.state = ws_state(ws);
     p.ntiles = ntiles;

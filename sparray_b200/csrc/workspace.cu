@@ -98,8 +98,10 @@ int workspace_reserve_accum(spb_workspace* ws, size_t bytes, cudaStream_t stream
 // meet the words of the previous replay tagged with the very same epoch.  While the stream is being
 // captured, the words the call asked for (workspace_reserve / _state16 just before) are therefore wiped by
 // a memset node in front of the launch: a replayed chain is self-contained.
-int workspace_next_epoch(spb_workspace* ws, cudaStream_t stream, uint32_t* epoch) {
-    if (capturing(stream)) {
+// wipe_in_capture = false: the caller's kernels do not read look-back words, or a producer launch of the
+// same chain wipes them.
+int workspace_next_epoch(spb_workspace* ws, cudaStream_t stream, uint32_t* epoch, bool wipe_in_capture) {
+    if (wipe_in_capture && capturing(stream)) {
         if (ws->last_state_bytes)
             SPB_CUDA_TRY(cudaMemsetAsync((char*)ws->dev + kWsMiscBytes, 0, ws->last_state_bytes, stream));
         if (ws->state16 && ws->last_state16_bytes)

@@ -19,9 +19,10 @@ Deliberate divergences from the reference:
   * results whose size depends on the data are lazily counted: the element count is read back from
     the device when ``indices`` / ``data`` / ``nnz`` are first looked at, not when the op returns
     (invisible to callers; it keeps chains such as ``(a * b).sum(axis=2)`` free of host waits);
-  * branches whose RESULT is dense by nature in the reference and that involve no dense
-    operand (sparse + nonzero scalar, sparse / sparse, sparse ** 0, ...) are out of the
-    hot-path scope and raise NotImplementedError; fancy assignment raises like the reference.
+  * branches whose RESULT is dense by nature in the reference (sparse + nonzero scalar, sparse / sparse,
+    sparse ** 0, comparisons that are true at zero, ...) return the same dense ndarray with the same
+    warning; the dense array is built and combined on the device (there is still no CPU arithmetic);
+    fancy assignment raises like the reference.
 """
 import numbers
 import warnings
@@ -486,7 +487,7 @@ class FlatSparray(_BaseSparray):
                 return self._scalar_map(op + "_s", other, compare=True)
             kind = "nonzero scalar" if other != 0 else "0"
             warnings.warn("FlatSparray %s %s densifies" % (op_symbol, kind), _EfficiencyWarning)
-            raise NotImplementedError("densifying comparison is out of sparray_b200's scope")
+            return self._dense_scalar_map(op + "_s", other, compare=True)           # ufunc(self.toarray(), other)
         lhs, rhs = self._handle_broadcasting(other)
         if isinstance(rhs, FlatSparray):
             return lhs._pairwise_sparray(rhs, op)
@@ -497,7 +498,7 @@ class FlatSparray(_BaseSparray):
             if other == 0:
                 return self.copy()
             warnings.warn("FlatSparray + nonzero scalar densifies", _EfficiencyWarning)
-            raise NotImplementedError("densifying add is out of sparray_b200's scope")
+            return self._dense_add_scalar(other)                                     # self.toarray() + other
         lhs, rhs = self._handle_broadcasting(other)
         if isinstance(rhs, FlatSparray):
             return lhs._pairwise_sparray(rhs, "add")
@@ -523,8 +524,12 @@ class FlatSparray(_BaseSparray):
         return lhs._pairwise_dense2sparse(rhs, "mul")
 
     def _divide(self, other, div_func="divide", rdivide=False):            # flat.py:520-536
-        if (ss is not None and ss.issparse(other)) or isinstance(other, FlatSparray) or rdivide:
-            raise NotImplementedError("this division densifies in the reference (flat.py:522-527); out of scope")
+        if ss is not None and ss.issparse(other):
+            other = FlatSparray.from_spmatrix(other)
+        if isinstance(other, FlatSparray) or rdivide:
+            # a sparse divisor (or a reflected division) cannot keep sparsity: dense result, computed on the
+            # device (flat.py:520-527)
+            return self._dense_divide(other, div_func, rdivide)
         if _is_scalar(other):
             if div_func in ("true_divide", "divide"):
                 return self.__mul__(1. / other)                            # flat.py:528-529
@@ -544,10 +549,29 @@ class FlatSparray(_BaseSparray):
         if self.shape[ax1] != oshape[ax2]:
             raise ValueError("shapes %s and %s not aligned" % (self.shape, oshape))
         nrows = self._size() // self.shape[ax1] if self.shape[ax1] else 0
+        if ss is not None and ss.issparse(other):
+            other = FlatSparray.from_spmatrix(other)
+        if isinstance(other, FlatSparray) and len(oshape) >= 2:
+            # sparse . sparse (flat.py:545-561): SpGEMM on the sorted flat layout -- expand / sort / compress
+            # instead of the reference's COO -> scipy CSR matmul -> from_spmatrix detour
+            out_shape = tuple(self.shape[:-1]) + oshape[:ax2] + oshape[ax2 + 1:]
+            if ax2 != 0:                                                   # bring the contracted axis first
+                other = other.transpose(*((ax2,) + tuple(range(ax2)) + tuple(range(ax2 + 1, len(oshape)))))
+            k = self.shape[ax1]
+            ncols = int(np.prod(other.shape[1:], dtype=object))
+            vdt = dt.promote(self.data.dtype, other.data.dtype)
+            if vdt in (torch.bool, torch.uint8, torch.int8, torch.int16):
+                vdt = torch.int32 if vdt != torch.bool else torch.int32
+            a_val = self.data if self.data.dtype == vdt else _k.cast(self.data, vdt)
+            b_val = other.data if other.data.dtype == vdt else _k.cast(other.data, vdt)
+            idx, val = _k.spgemm(self.indices, a_val, nrows, k, other.indices, b_val, ncols)
+            want = dt.promote(self.data.dtype, other.data.dtype)
+            if val.dtype != want:
+                val = _k.cast(val, want)
+            return FlatSparray(idx, val, shape=out_shape, is_canonical=True)
         if len(oshape) == 2:
-            # matrix operand: one SpMV per column (dense result, like flat.py:568 without densifying self);
-            # a sparse matrix operand is densified column-wise the same way (the reference goes through scipy)
-            dense = other.todense_device() if isinstance(other, FlatSparray) else _to_device_nd(other)
+            # dense matrix operand: one SpMV per column (dense result, like flat.py:568 without densifying self)
+            dense = _to_device_nd(other)
             cols = dense.t().contiguous()
             vdt = dt.promote(self.data.dtype, cols.dtype)
             out = torch.empty((oshape[1], nrows), dtype=vdt if vdt.is_floating_point else torch.float64,
@@ -555,11 +579,9 @@ class FlatSparray(_BaseSparray):
             for j in range(oshape[1]):
                 out[j] = _k.spmv(self.indices, self.data, self.shape[ax1], nrows, cols[j], vdt)
             res = out.t().contiguous().reshape(self.shape[:-1] + (oshape[1],))
-            if isinstance(other, FlatSparray):
-                return FlatSparray.from_ndarray(res)
             return res.cpu().numpy()
         if len(oshape) != 1:
-            raise NotImplementedError("dot with an operand of more than two dimensions is out of scope")
+            raise NotImplementedError("dot with a dense operand of more than two dimensions is out of scope")
         if isinstance(other, FlatSparray):                                 # sparse vector: sparse result
             x = other.todense_device().reshape(-1)
             vdt = dt.promote(self.data.dtype, x.dtype)
@@ -570,6 +592,10 @@ class FlatSparray(_BaseSparray):
         x = _to_device(other)
         vdt = dt.promote(self.data.dtype, x.dtype)
         y = _k.spmv(self.indices, self.data, self.shape[ax1], nrows, x, vdt)
+        if not vdt.is_floating_point:
+            # numpy's dot of integer operands is an integer (flat.py:566,568); the float64 accumulation is
+            # exact below 2^53
+            y = _k.cast(y, vdt if vdt != torch.bool else torch.int64)
         if len(self.shape) == 1:
             return y.cpu().numpy()[0]                                      # flat.py:564-566
         return y.reshape(self.shape[:-1]).cpu().numpy()                    # dense rhs -> dense result
@@ -577,17 +603,19 @@ class FlatSparray(_BaseSparray):
     def __pow__(self, exponent):                                           # flat.py:570-578
         if exponent == 0:
             warnings.warn("FlatSparray ** 0 densifies", _EfficiencyWarning)
-            raise NotImplementedError("densifying power is out of sparray_b200's scope")
+            return np.ones(self.shape, dtype=self.dtype)
         elif exponent < 0:
             warnings.warn("FlatSparray ** negative exponent densifies", _EfficiencyWarning)
-            raise NotImplementedError("densifying power is out of sparray_b200's scope")
+            if self.dtype.kind in "iub" and isinstance(exponent, (int, np.integer)):
+                raise ValueError("Integers to negative integer powers are not allowed.")
+            return self._dense_scalar_map("pow_s", exponent)                        # self.toarray() ** exponent
         return self._scalar_map("pow_s", exponent)
 
     def _with_data(self, data):                                            # flat.py:580-581
         return FlatSparray(self.indices.clone(), data, self.shape, is_canonical=True)
 
-    def _scalar_map(self, op, scalar, compare=False):
-        """data (op) python/numpy scalar with numpy's result dtype."""
+    def _map_values(self, data, op, scalar, compare=False):
+        """data (op) python/numpy scalar with numpy's result dtype, on any device vector of this array's dtype."""
         if isinstance(scalar, (torch.Tensor, np.ndarray)):
             scalar = scalar.item()
         if isinstance(scalar, complex) or np.iscomplexobj(scalar):
@@ -601,23 +629,91 @@ class FlatSparray(_BaseSparray):
             res = np.result_type(np_dt, scalar)
             if res == np.bool_:
                 res = np.dtype(np.int64)
-        data = self.data
         tdt = dt.torch_dtype(res)
         if data.dtype != tdt:
             data = _k.cast(data, tdt)
-        return self._with_data(_k.unary_map(op, data, scalar))
+        return _k.unary_map(op, data, scalar)
+
+    def _scalar_map(self, op, scalar, compare=False):
+        """data (op) python/numpy scalar with numpy's result dtype."""
+        return self._with_data(self._map_values(self.data, op, scalar, compare))
+
+    # -- branches whose result is dense by nature (flat.py:478-481,494-496,520-527,570-577,592-593,604-605):
+    #    the reference computes ufunc(self.toarray(), ...) on the host; here the dense array is built and
+    #    combined on the device and comes back as the ndarray the reference returns
+    def _dense_scalar_map(self, op, scalar, compare=False):
+        dense = self.todense_device().reshape(-1)
+        return self._map_values(dense, op, scalar, compare).reshape(self.shape).cpu().numpy()
+
+    def _dense_add_scalar(self, scalar):
+        if isinstance(scalar, complex) or np.iscomplexobj(scalar):
+            raise TypeError("complex values are not supported by the sparray_b200 CUDA kernels")
+        res = np.result_type(self.dtype, scalar)
+        if res == np.bool_:
+            res = np.dtype(np.int64)
+        tdt = dt.torch_dtype(res)
+        dense = self.todense_device().reshape(-1)
+        if dense.dtype != tdt:
+            dense = _k.cast(dense, tdt)
+        fill = torch.full_like(dense, scalar)                    # a constant operand: plumbing, the add is ours
+        return _k.binary_map("add", dense, fill).reshape(self.shape).cpu().numpy()
+
+    def _dense_divide(self, other, div_func, rdivide):
+        mine = self.todense_device()
+        if isinstance(other, FlatSparray):
+            theirs = other.todense_device()
+        elif _is_scalar(other):
+            theirs = torch.full_like(mine, other, dtype=dt.torch_dtype(np.result_type(self.dtype, other)))
+        else:
+            theirs = _to_device_nd(other)
+        bshape = tuple(int(x) for x in np.broadcast_shapes(tuple(mine.shape), tuple(theirs.shape)))
+        a = mine.expand(bshape).contiguous().reshape(-1)
+        b = theirs.expand(bshape).contiguous().reshape(-1)
+        common = dt.promote(a.dtype, b.dtype)
+        if div_func in ("true_divide", "divide") and not common.is_floating_point:
+            common = torch.float64
+        a = a if a.dtype == common else _k.cast(a, common)
+        b = b if b.dtype == common else _k.cast(b, common)
+        if rdivide:
+            a, b = b, a
+        op = "floor_divide" if div_func == "floor_divide" else "divide"
+        with np.errstate(all="ignore"):
+            return _k.binary_map(op, a, b).reshape(bshape).cpu().numpy()
+
+    def _rdot(self, other):                                                # base.py:79-82: other.dot(self.toarray())
+        """dense . sparse -> dense, as (sparse^T . dense^T)^T: SpMV passes over the transposed array."""
+        arr = np.asarray(other)
+        if arr.ndim == 1:
+            return self.transpose().dot(arr)
+        lead = arr.shape[:-1]
+        res = self.transpose().dot(arr.reshape(-1, arr.shape[-1]).T)       # (n, rows)
+        return np.ascontiguousarray(res.T).reshape(lead + tuple(self.shape[1:]))
+
+    def __rmatmul__(self, other):
+        return self._rdot(other)
 
     def _float_map(self, op):
+        """np.<op>(data) with the result dtype the installed numpy gives (flat.py:722-739 applies the ufunc to
+        `data`): integer data stays integer for sign / floor / ceil / trunc (numpy >= 2.1), everything else is
+        computed in floating point."""
         data = self.data
-        if not data.dtype.is_floating_point:
-            data = _k.cast(data, torch.float64)
-        return self._with_data(_k.unary_map(op, data))
+        if data.dtype.is_floating_point:
+            return self._with_data(_k.unary_map(op, data))
+        res = getattr(np, op)(np.zeros(1, dtype=self.dtype)).dtype
+        if res.kind in "iub" and op in ("floor", "ceil", "trunc"):
+            out = data.clone()                           # the identity on integers
+        elif res.kind in "iu" and op == "sign" and data.dtype in (torch.int32, torch.int64):
+            out = _k.unary_map(op, data)
+        else:
+            out = _k.unary_map(op, _k.cast(data, torch.float64))
+        want = dt.torch_dtype(res)
+        return self._with_data(out if out.dtype == want else _k.cast(out, want))
 
     def minimum(self, other):                                              # flat.py:583-593
         if _is_scalar(other) and other >= 0:
             return self._scalar_map("min_s", other)
         if _is_scalar(other):
-            raise NotImplementedError("minimum with a negative scalar densifies; out of scope")
+            return self._dense_scalar_map("min_s", other)                            # np.minimum(self.toarray(), other)
         lhs, rhs = self._handle_broadcasting(other)
         if isinstance(rhs, FlatSparray):
             return lhs._pairwise_sparray(rhs, "minimum")
@@ -627,7 +723,7 @@ class FlatSparray(_BaseSparray):
         if _is_scalar(other) and other <= 0:
             return self._scalar_map("max_s", other)
         if _is_scalar(other):
-            raise NotImplementedError("maximum with a positive scalar densifies; out of scope")
+            return self._dense_scalar_map("max_s", other)                            # np.maximum(self.toarray(), other)
         lhs, rhs = self._handle_broadcasting(other)
         if isinstance(rhs, FlatSparray):
             return lhs._pairwise_sparray(rhs, "maximum")

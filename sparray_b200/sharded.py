@@ -124,7 +124,8 @@ def sampled_splitters(local_idx, shape, group=None, ops=None, samples_per_rank=2
     n = local_idx.numel()
     take = min(samples_per_rank, n)
     if take:
-        pos = torch.linspace(0, n - 1, take, device=local_idx.device).long()
+        # evenly spaced positions in exact integer arithmetic (a float32 linspace overshoots n - 1 beyond 2^24)
+        pos = (torch.arange(take, device=local_idx.device, dtype=torch.int64) * (n - 1)) // max(take - 1, 1)
         sample = local_idx[pos]
     else:
         sample = local_idx[:0]
@@ -151,11 +152,17 @@ class ShardedFlatSparray:
     are kept until ``indices`` / ``data`` / ``nnz_local`` are looked at, so a chain such as
     ``(a * b).sum(axis)`` on co-partitioned, row-aligned shards never waits for the host."""
 
-    def __init__(self, indices, data, shape, splitters, group=None, ops=None, _pending=None):
+    def __init__(self, indices, data, shape, splitters, group=None, ops=None, _pending=None, _like=None):
         self._indices, self._data, self._pending = indices, data, _pending
+        self.group = group
+        if _like is not None:
+            # derived from another shard of the same group: skip the (slow) process-group queries and the
+            # re-validation of shape / splitters that the parent already did
+            self.shape, self.splitters = shape, splitters
+            self.ops, self.rank, self.world = _like.ops, _like.rank, _like.world
+            return
         self.shape = tuple(int(s) for s in shape)
         self.splitters = [int(s) for s in splitters]
-        self.group = group
         self.ops = ops if ops is not None else CudaOps()
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -188,11 +195,11 @@ class ShardedFlatSparray:
         return int(t.item())
 
     def _like(self, indices, data, shape=None, splitters=None, cnt=None):
+        shape = self.shape if shape is None else tuple(int(s) for s in shape)
+        splitters = self.splitters if splitters is None else [int(s) for s in splitters]
         if cnt is not None:
-            return ShardedFlatSparray(None, None, shape or self.shape, splitters or self.splitters, self.group,
-                                      self.ops, _pending=(indices, data, cnt))
-        return ShardedFlatSparray(indices, data, shape or self.shape, splitters or self.splitters,
-                                  self.group, self.ops)
+            return ShardedFlatSparray(None, None, shape, splitters, self.group, _pending=(indices, data, cnt), _like=self)
+        return ShardedFlatSparray(indices, data, shape, splitters, self.group, _like=self)
 
     # ---- co-partitioned / repartitioned binops -------------------------------------------------------
     def _binop(self, other, kind, op):
@@ -322,9 +329,7 @@ class ShardedFlatSparray:
         # an output row cut by a splitter belongs to the rank on the right of the cut
         new_split = [(s // block) * inner for s in sp[:-1]] + [cells_total]
         if all(s % block == 0 for s in sp[1:-1]):
-            return ShardedFlatSparray(keys, sums, new_shape, new_split, self.group, self.ops,
-                                      _pending=None) if cnt is None else \
-                ShardedFlatSparray(None, None, new_shape, new_split, self.group, self.ops, _pending=(keys, sums, cnt))
+            return self._like(keys, sums, shape=new_shape, splitters=new_split, cnt=cnt)
         if cnt is not None:
             n = int(cnt.item())
             keys, sums = keys[:n], sums[:n]

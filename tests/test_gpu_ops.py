@@ -564,3 +564,83 @@ def test_cuda_graph_capture_of_a_chain(sp):
                 np.testing.assert_array_equal(val[:n].cpu().numpy(), want.data)
             else:
                 np.testing.assert_allclose(val[:n].cpu().numpy(), want.data, rtol=1e-5, atol=1e-5)
+
+
+def test_spgemm_vs_scipy(sp):
+    """sparse . sparse (flat.py:545-561: the reference goes reshape -> COO -> scipy CSR matmul -> from_spmatrix):
+    the expand / sort / compress kernels against scipy's product, 2-D and N-D operands, several dtypes,
+    empty rows, an all-empty operand, explicit zeros, a scipy operand."""
+    import scipy.sparse as ss
+    rng = np.random.default_rng(41)
+    for (m, k, n, da, db, dtype) in [(300, 200, 150, 0.05, 0.04, np.float64), (1000, 800, 900, 0.01, 0.01, np.float32),
+                                     (64, 4096, 32, 0.02, 0.3, np.float64), (50, 40, 30, 0.2, 0.2, np.int64),
+                                     (50, 40, 30, 0.2, 0.2, np.int32)]:
+        Am = ss.random(m, k, density=da, random_state=int(rng.integers(1 << 30)), format="csr", dtype=np.float64)
+        Bm = ss.random(k, n, density=db, random_state=int(rng.integers(1 << 30)), format="csr", dtype=np.float64)
+        if np.dtype(dtype).kind == "i":
+            Am.data = np.rint(Am.data * 20) + 1
+            Bm.data = np.rint(Bm.data * 20) + 1
+        Am, Bm = Am.astype(dtype), Bm.astype(dtype)
+        A, B = sp.FlatSparray.from_spmatrix(Am), sp.FlatSparray.from_spmatrix(Bm)
+        C = A.dot(B)
+        want = (Am @ Bm).tocoo()
+        want.sum_duplicates()
+        assert isinstance(C, sp.FlatSparray) and C.shape == (m, n) and C.dtype == np.dtype(dtype)
+        wi = want.row.astype(np.int64) * n + want.col
+        order = np.argsort(wi)
+        np.testing.assert_array_equal(to_np(C.indices), wi[order])
+        if np.dtype(dtype).kind == "i":
+            np.testing.assert_array_equal(to_np(C.data), want.data[order])
+        else:
+            tol = 1e-5 if dtype == np.float32 else 1e-12
+            np.testing.assert_allclose(to_np(C.data), want.data[order], rtol=tol, atol=tol)
+        np.testing.assert_array_equal(to_np((A @ B).indices), wi[order])
+        # a scipy operand on the right (flat.py:546)
+        np.testing.assert_array_equal(to_np(A.dot(Bm).indices), wi[order])
+    # N-D operands: contraction of self's last axis with other's second-to-last (flat.py:539-556)
+    T = rng.standard_normal((4, 5, 20)); T[rng.random(T.shape) < 0.6] = 0
+    U = rng.standard_normal((3, 20, 6)); U[rng.random(U.shape) < 0.5] = 0
+    r = sp.FlatSparray.from_ndarray(T).dot(sp.FlatSparray.from_ndarray(U))
+    assert r.shape == (4, 5, 3, 6)
+    np.testing.assert_allclose(r.toarray(), T.dot(U), rtol=1e-12, atol=1e-12)
+    # an operand with nothing stored
+    Z = sp.FlatSparray([], np.zeros(0), shape=(20, 6), is_canonical=True)
+    r = sp.FlatSparray.from_ndarray(T).dot(Z)
+    assert r.shape == (4, 5, 6) and r.nnz == 0
+
+
+def test_densifying_branches_return_dense_results(sp):
+    """The branches whose result is dense by nature (flat.py:478-481,494-496,520-527,570-577,592-593,604-605)
+    return the ndarray the reference returns, with the reference's SparseEfficiencyWarning."""
+    import warnings
+    rng = np.random.default_rng(77)
+    D = rng.standard_normal((7, 9)); D[rng.random(D.shape) < 0.6] = 0
+    E = rng.standard_normal((7, 9)); E[rng.random(E.shape) < 0.6] = 0
+    A, B = sp.FlatSparray.from_ndarray(D), sp.FlatSparray.from_ndarray(E)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        np.testing.assert_array_equal(A + 2.5, D + 2.5)
+        np.testing.assert_array_equal(A - 1, D - 1)
+        np.testing.assert_array_equal(A < 1, D < 1)
+        np.testing.assert_array_equal(A >= 0, D >= 0)
+        np.testing.assert_array_equal(A == 0, D == 0)
+        np.testing.assert_array_equal(A != 3, D != 3)
+        np.testing.assert_array_equal(A ** 0, D ** 0)
+        with np.errstate(all="ignore"):
+            np.testing.assert_array_equal(A ** -2, D ** -2.0)
+        assert sum("densifies" in str(x.message) for x in w) == 8, [str(x.message) for x in w]
+    np.testing.assert_array_equal(A.minimum(-0.5), np.minimum(D, -0.5))
+    np.testing.assert_array_equal(A.maximum(0.25), np.maximum(D, 0.25))
+    with np.errstate(all="ignore"):
+        np.testing.assert_array_equal(A / B, D / E)                      # nan / inf where the divisor is empty
+        np.testing.assert_array_equal(A // B, D // E)
+        np.testing.assert_array_equal(2.0 / A, 2.0 / D)
+        np.testing.assert_array_equal(E / A, E / D)
+    I = sp.FlatSparray.from_ndarray(np.arange(12).reshape(3, 4) % 3)
+    np.testing.assert_array_equal(I + 1, np.arange(12).reshape(3, 4) % 3 + 1)
+    with pytest.raises(ValueError):
+        I ** -1
+    # reflected matmul / _rdot (base.py:79-82)
+    M = rng.standard_normal((5, 7))
+    np.testing.assert_allclose(A._rdot(M), M.dot(D), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(M @ A, M @ D, rtol=1e-12, atol=1e-12)
