@@ -258,9 +258,9 @@ int spb_axis_sum_window(int dtype, const int64_t* idx, const void* val, int64_t 
                         spb_workspace* ws, spb_stream_t stream);
 
 /* The two halves of spb_axis_sum_dense on caller-owned buffers, for the sharded axis sum of
- * SURVEY.md section 8(e) (dense per-GPU accumulators + all-reduce): acc = cells doubles,
- * touched = cells flag bytes padded to a multiple of 64 and 16-byte aligned, both zeroed by the
- * caller.  spb_emit_touched emits the touched cells of [cell_lo, cell_hi) in key order (absolute cell
+ * SURVEY.md section 8(e) (dense per-GPU accumulators + all-reduce): acc = cells doubles padded to
+ * a multiple of 16 and 16-byte aligned, touched = cells flag bytes padded to a multiple of 64 and 16-byte
+ * aligned, both zeroed by the caller.  spb_emit_touched emits the touched cells of [cell_lo, cell_hi) in key order (absolute cell
  * numbers; cell_lo a multiple of 64; out_idx / out_sums: cell_hi - cell_lo slots) and zeroes them. */
 int spb_axis_accumulate(int dtype, const int64_t* idx, const void* val, int64_t n,
                         int ndim, const int64_t* in_strides_host, const int64_t* out_strides_host,

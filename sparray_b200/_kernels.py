@@ -340,7 +340,11 @@ def _use_dense(n, cells, last, n_dev):
         return True
     if not n or cells > DENSE_SUM_MAX_CELLS:
         return False
-    return cells <= (4 if last else 64) * n + _l2_resident_cells(_cur_dev())
+    if last:
+        # the input is already grouped: beyond an L2-resident slab the one-pass segmented reduce wins
+        # (config-2 operand, 16.7 M cells: 198 us against 213 us)
+        return cells <= _l2_resident_cells(_cur_dev())
+    return cells <= 64 * n + _l2_resident_cells(_cur_dev())
 
 
 def sum_axis(idx, val, shape, axis, n_dev=None, window=None):
@@ -401,7 +405,7 @@ def axis_accumulate(idx, val, in_strides, out_strides, cells):
     to 64]) holding this shard's contributions; to be all-reduced (SUM / MAX) across ranks."""
     require_cuda()
     cells = int(cells)
-    acc = torch.zeros(cells, dtype=torch.float64, device=idx.device)
+    acc = torch.zeros((cells + 15) // 16 * 16, dtype=torch.float64, device=idx.device)   # padded: 16-byte pair loads
     touched = torch.zeros((cells + 63) // 64 * 64, dtype=torch.uint8, device=idx.device)
     ndim, ins, outs, _keep = _stride_args(tuple(in_strides), tuple(out_strides))
     check(lib.spb_axis_accumulate(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), idx.numel(), ndim, ins, outs, cells,

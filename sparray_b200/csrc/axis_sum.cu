@@ -243,10 +243,12 @@ __global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict_
         const unsigned obits = __shfl_sync(0xffffffffu, bits, owner);
         if (r < warp_total) {
             const int k = (int)__fns(obits, 0, r - owner_excl + 1);
-            const int64_t cell = warp_first + (int64_t)owner * kSelCells + k;
-            out_idx[warp_off + r] = key_base + cell;
-            out_val[warp_off + r] = acc[cell];
-            acc[cell] = 0.0;
+            const int local = owner * kSelCells + k;
+            out_idx[warp_off + r] = key_base + warp_first + local;
+            // one gather per emitted element (measured against loading every cell of a touched thread up
+            // front and emitting from shared memory: 111 vs 126 us on the config-2 operand)
+            out_val[warp_off + r] = acc[warp_first + local];
+            acc[warp_first + local] = 0.0;
         }
     }
 }

@@ -15,23 +15,24 @@ struct Rekey {
     int pow2;                             // every in_div and every non-zero out_mul is a power of two
     FastDiv in_div[kMaxRekeyDims];        // C-order stride of (merged) axis group ax in the old shape
     int64_t out_mul[kMaxRekeyDims];       // its stride in the new shape; 0 = group dropped
-    int out_shift[kMaxRekeyDims];         // pow2: log2(out_mul), -1 = dropped
-    uint64_t gmask[kMaxRekeyDims];        // pow2: (size of the group) - 1; all ones for the outermost group
+    // pow2: the groups that survive, as bit fields that move: new |= ((old >> f_in) & f_mask) << f_out
+    int nfields;
+    int f_in[kMaxRekeyDims];
+    int f_out[kMaxRekeyDims];
+    uint64_t f_mask[kMaxRekeyDims];       // (size of the group) - 1; all ones for the outermost group
 };
+
+template <int NF>
+__device__ __forceinline__ int64_t move_fields(uint64_t idx, const Rekey& r) {
+    uint64_t acc = 0;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) acc |= ((idx >> r.f_in[f]) & r.f_mask[f]) << r.f_out[f];
+    return (int64_t)acc;
+}
 
 // NDIM known at compile time: straight-line code, no per-axis predicates
 template <int NDIM>
 __device__ __forceinline__ int64_t apply_rekey_n(uint64_t idx, const Rekey& r) {
-    if (r.pow2) {
-        // power-of-two shapes (BASELINE configs 2, 3, 5): every group is a bit field that moves
-        uint64_t acc = 0;
-#pragma unroll
-        for (int ax = 0; ax < NDIM; ++ax) {
-            const uint64_t q = (idx >> r.in_div[ax].shift) & r.gmask[ax];
-            if (r.out_shift[ax] >= 0) acc |= q << r.out_shift[ax];
-        }
-        return (int64_t)acc;
-    }
     uint64_t rem = idx;
     int64_t acc = 0;
 #pragma unroll
@@ -44,8 +45,23 @@ __device__ __forceinline__ int64_t apply_rekey_n(uint64_t idx, const Rekey& r) {
 }
 
 __device__ __forceinline__ int64_t apply_rekey(int64_t idx, const Rekey& r) {
+    if (r.ndim == 0) return idx;
+    if (r.pow2) {
+        // power-of-two shapes (BASELINE configs 2, 3, 5): every surviving group is a bit field that moves;
+        // dropped groups cost nothing
+        switch (r.nfields) {
+            case 0: return 0;
+            case 1: return move_fields<1>((uint64_t)idx, r);
+            case 2: return move_fields<2>((uint64_t)idx, r);
+            case 3: return move_fields<3>((uint64_t)idx, r);
+            case 4: return move_fields<4>((uint64_t)idx, r);
+            default: break;
+        }
+        uint64_t acc = 0;
+        for (int f = 0; f < r.nfields; ++f) acc |= (((uint64_t)idx >> r.f_in[f]) & r.f_mask[f]) << r.f_out[f];
+        return (int64_t)acc;
+    }
     switch (r.ndim) {
-        case 0: return idx;
         case 1: return apply_rekey_n<1>((uint64_t)idx, r);
         case 2: return apply_rekey_n<2>((uint64_t)idx, r);
         case 3: return apply_rekey_n<3>((uint64_t)idx, r);
@@ -73,18 +89,23 @@ inline int make_rekey(Rekey& rk, int ndim, const int64_t* in_strides, const int6
         if (in_strides[ax] < 1 || out_strides[ax] < 0) return SPB_ERR_BAD_ARG;
         rk.in_div[ax] = make_fastdiv((uint64_t)in_strides[ax]);
         rk.out_mul[ax] = out_strides[ax];
-        rk.out_shift[ax] = -1;
-        rk.gmask[ax] = ax == 0 ? ~0ull : (uint64_t)(in_strides[ax - 1] / in_strides[ax]) - 1;
         const uint64_t m = (uint64_t)out_strides[ax];
         if (rk.in_div[ax].magic != 0) rk.pow2 = 0;
-        if (m) {
-            if (m & (m - 1)) rk.pow2 = 0;
-            int s = 0;
-            while ((1ull << s) < m) ++s;
-            rk.out_shift[ax] = s;
-        }
+        if (m && (m & (m - 1))) rk.pow2 = 0;
     }
     if (ndim && in_strides[ndim - 1] != 1) return SPB_ERR_BAD_ARG;
+    if (rk.pow2) {
+        for (int ax = 0; ax < ndim; ++ax) {
+            const uint64_t m = (uint64_t)out_strides[ax];
+            if (!m) continue;                     // dropped group
+            int s = 0;
+            while ((1ull << s) < m) ++s;
+            const int f = rk.nfields++;
+            rk.f_in[f] = (int)rk.in_div[ax].shift;
+            rk.f_out[f] = s;
+            rk.f_mask[f] = ax == 0 ? ~0ull : (uint64_t)(in_strides[ax - 1] / in_strides[ax]) - 1;
+        }
+    }
     return SPB_OK;
 }
 

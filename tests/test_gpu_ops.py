@@ -627,7 +627,7 @@ def test_densifying_branches_return_dense_results(sp):
         np.testing.assert_array_equal(A != 3, D != 3)
         np.testing.assert_array_equal(A ** 0, D ** 0)
         with np.errstate(all="ignore"):
-            np.testing.assert_array_equal(A ** -2, D ** -2.0)
+            np.testing.assert_allclose(A ** -2, D ** -2.0, rtol=1e-14)       # CUDA pow: within an ulp of numpy's
         assert sum("densifies" in str(x.message) for x in w) == 8, [str(x.message) for x in w]
     np.testing.assert_array_equal(A.minimum(-0.5), np.minimum(D, -0.5))
     np.testing.assert_array_equal(A.maximum(0.25), np.maximum(D, 0.25))
