@@ -269,6 +269,18 @@ int spb_emit_touched(double* acc, uint8_t* touched, int64_t cell_lo, int64_t cel
                      int64_t* out_idx, double* out_sums, int64_t* out_count,
                      spb_workspace* ws, spb_stream_t stream);
 
+/* sum(axis) in one streaming pass, no dense accumulator array and no sort (csrc/slab_sum.cu): applies when
+ * the elements feeding a bounded set of output cells are contiguous in the sorted input -- the reduced axis
+ * is the last one, or the axes behind it span at most 4096 cells -- and the array is not extremely sparse.
+ * total_cells = prod(shape); slab_cells = shape[axis] * suffix; suffix = prod(shape[axis+1:]).
+ * spb_axis_sum_slab_ok answers (1 / 0) whether spb_axis_sum_slab accepts these sizes (it returns
+ * SPB_ERR_UNSUPPORTED otherwise).  out_idx / out_sums: min(n, total_cells / shape[axis]) slots; float64 sums,
+ * keys in the reduced shape, in order; elements whose flat index is >= total_cells are ignored. */
+int spb_axis_sum_slab_ok(int64_t n, int64_t total_cells, int64_t slab_cells, int64_t suffix);
+int spb_axis_sum_slab(int dtype, const int64_t* idx, const void* val, int64_t n, int64_t total_cells,
+                      int64_t slab_cells, int64_t suffix, int64_t* out_idx, double* out_sums,
+                      int64_t* out_count, spb_workspace* ws, spb_stream_t stream);
+
 /* ---- 6. __getitem__: flat.py:254-325, 366-393 ---------------------------------- */
 
 /* ints + slices (flat.py:270-274) without materialising the box: keeps the stored

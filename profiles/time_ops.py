@@ -21,6 +21,10 @@ ai, av = synth(10_700_000, 256 * 256 * 256 * 64, torch.float32, 1)
 A = sp.FlatSparray(ai, av, shape=shape, is_canonical=True)
 print("sum_axis3 (last) f32 10.7M: %.0f us" % t(lambda: A.sum(axis=3)))
 print("sum_axis2 f32 10.7M: %.0f us" % t(lambda: A.sum(axis=2)))
+for ax in (3, 2, 1):
+    g = k.slab_geometry(shape, ax)
+    if sp._lib.lib.spb_axis_sum_slab_ok(ai.numel(), *g):
+        print("  slab kernels, axis %d: %.0f us" % (ax, t(lambda: k.axis_sum_slab(ai, av, g, ai.numel()))))
 print("  reduce_by_key(div 64) = last-axis sum without the dense slab: %.0f us" % t(lambda: k.reduce_by_key(ai, av, 64)))
 print("  sum_axis1 f32 10.7M: %.0f us ; sum_axis0: %.0f us" % (t(lambda: A.sum(axis=1)), t(lambda: A.sum(axis=0))))
 print("transpose 3210 f32 10.7M: %.0f us" % t(lambda: A.transpose(3, 2, 1, 0)))

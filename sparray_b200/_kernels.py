@@ -363,6 +363,12 @@ def sum_axis(idx, val, shape, axis, n_dev=None, window=None):
     total_cells = _plan.prod(shape) // max(int(shape[axis]), 1)
     lo, hi = (0, total_cells) if window is None else (int(window[0]), int(window[1]))
     cells = hi - lo
+    if n_dev is None and window is None and n:
+        # one streaming pass over whole slabs of the leading coordinates (csrc/slab_sum.cu) when the library
+        # says the shape and fill allow it: neither a dense accumulator array nor a sort
+        slab = slab_geometry(shape, axis)
+        if slab is not None and _prefer_slab(n, total_cells, slab[2]) and lib.spb_axis_sum_slab_ok(n, *slab):
+            return axis_sum_slab(idx, val, slab, min(n, total_cells))
     if plan[0] == "last":
         if _use_dense(n, cells, True, n_dev):
             # the elements of an output cell are contiguous: warp-aggregated atomics into the dense accumulator
@@ -374,6 +380,35 @@ def sum_axis(idx, val, shape, axis, n_dev=None, window=None):
     assert n_dev is None
     keys, vals = rekey_sort(idx, val, in_s, out_s, 1, bits)
     return reduce_by_key(keys, vals, 1) + (None,)
+
+
+def _prefer_slab(n, out_cells, suffix):
+    """Measured on the config-2 / config-4 operands: with the reduced axis last the slab kernels win unless the
+    runs are long (>= 8 stored elements per output cell: the lane-pre-reducing dense kernel is faster there);
+    for other axes they win once the dense accumulators would not stay in L2."""
+    if suffix == 1:
+        return n < 8 * out_cells
+    return out_cells > _l2_resident_cells(_cur_dev())
+
+
+def slab_geometry(shape, axis):
+    """(prod(shape), shape[axis] * suffix, suffix) with suffix = prod(shape[axis+1:]); None for empty shapes."""
+    from . import _plan
+    total = _plan.prod(shape)
+    suffix = _plan.prod(shape[axis + 1:])
+    if total < 1 or total >= 1 << 62:
+        return None
+    return total, int(shape[axis]) * suffix, suffix
+
+
+def axis_sum_slab(idx, val, slab, cap):
+    require_cuda()
+    out_idx = torch.empty(cap, dtype=torch.int64, device=idx.device)
+    out_sums = torch.empty(cap, dtype=torch.float64, device=idx.device)
+    cnt = torch.empty(1, dtype=torch.int64, device=idx.device)
+    check(lib.spb_axis_sum_slab(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), idx.numel(), slab[0], slab[1], slab[2],
+                                ptr(out_idx), ptr(out_sums), ptr(cnt), workspace(), stream()))
+    return out_idx, out_sums, cnt
 
 
 @functools.lru_cache(maxsize=512)

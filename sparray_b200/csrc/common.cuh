@@ -256,6 +256,69 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* state, in
     return total;
 }
 
+// Two-level look-back.  The plain walk above moves 32 tiles per L2 round trip, and a tile can only stop at a
+// predecessor whose own walk is over: once tiles start faster than about 32 per round trip (a 2048-element tile
+// is ~5 ns of HBM time on a B200, a round trip ~500 ns) the distance to the nearest finished walk keeps
+// growing and the chain, not the memory system, sets the pace (measured: 30-55 tiles/us whatever the kernel
+// did per tile).  So the tiles are grouped in BLOCKS of 32 with one more state word each, behind the ntiles tile
+// words: the last tile of a block publishes the block's AGGREGATE as soon as the 31 counts before it are out
+// (no dependence on anybody's prefix), and its inclusive prefix when its own walk is over.  A walk is then:
+// one window over the earlier tiles of the own block, then windows of 32 BLOCK words (1024 tiles per round
+// trip).  Every wait is for a count that is published unconditionally: no chain.
+// Called by one full warp after the caller has published the tile's own word (aggregate; prefix for tile 0);
+// `total` is the tile's own count.  Not for tile 0.  Returns the exclusive prefix in every lane.
+__device__ __forceinline__ uint64_t wait_state(const uint64_t* p, uint32_t epoch) {
+    uint64_t w;
+    for (;;) {
+        w = ld_state(p);
+        if ((w >> 62) != 0 && (uint32_t)((w >> 48) & ((1u << kEpochBits) - 1)) == epoch) break;
+        __nanosleep(20);
+    }
+    return w;
+}
+
+__host__ __device__ inline int64_t lookback2_words(int64_t ntiles) { return ntiles + (ntiles >> 5) + 1; }
+
+__device__ __forceinline__ uint64_t lookback_exclusive_2level(uint64_t* state, int64_t ntiles, int64_t tile,
+                                                              uint32_t epoch, uint64_t total) {
+    const int lane = threadIdx.x & 31;
+    uint64_t* const blocks = state + ntiles;
+    const int64_t b = tile >> 5;
+    const int j = (int)(tile & 31);
+    uint64_t excl;
+    bool done;
+    {   // the earlier tiles of my own block
+        const bool in = lane < j;
+        uint64_t w = 0;
+        if (in) w = wait_state(state + (tile - 1 - lane), epoch);
+        const unsigned has_prefix = __ballot_sync(0xffffffffu, in && (w >> 62) == kStPrefix);
+        const int stop = has_prefix ? (__ffs(has_prefix) - 1) : 31;
+        uint64_t v = (in && lane <= stop) ? (w & kCountMask) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl = v;
+        done = has_prefix != 0;
+    }
+    // the block's aggregate goes out as soon as it is known
+    if (!done && j == 31 && lane == 0) st_state(blocks + b, pack_state(kStAgg, epoch, excl + total));
+    int64_t bb = b - 1;
+    while (!done) {
+        const int64_t q = bb - lane;
+        uint64_t w = pack_state(kStPrefix, epoch, 0);          // in front of block 0: an empty prefix
+        if (q >= 0) w = wait_state(blocks + q, epoch);
+        const unsigned has_prefix = __ballot_sync(0xffffffffu, (w >> 62) == kStPrefix);
+        const int stop = has_prefix ? (__ffs(has_prefix) - 1) : 31;
+        uint64_t v = lane <= stop ? (w & kCountMask) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        done = has_prefix != 0;
+        bb -= 32;
+    }
+    if (j == 31 && lane == 0) st_state(blocks + b, pack_state(kStPrefix, epoch, excl + total));
+    return excl;
+}
+
 // Block-wide variant for 256-thread CTAs: every thread inspects one predecessor tile, so a
 // whole wave of concurrently running tiles (persistent kernels: a few hundred) is covered in one
 // or two rounds instead of a dozen dependent warp-wide ones.  `scratch` = 24 ints (16-byte aligned) of shared

@@ -66,6 +66,11 @@ struct HistParams {
 };
 
 // ---- all digit histograms in one read --------------------------------------------------------
+// Four keys per thread are in flight per trip; a warp whose 32 keys share a digit (sorted input: the digit
+// is a function of a slowly changing coordinate) adds 32 with one shared-memory atomic instead of a 32-way
+// bank conflict.
+constexpr int kHistUnroll = 4;
+
 __global__ void __launch_bounds__(kSNT) radix_hist_kernel(const HistParams p) {
     __shared__ unsigned h[kMaxPasses * 256];
     for (int i = threadIdx.x; i < p.npasses * 256; i += kSNT) h[i] = 0;
@@ -73,34 +78,32 @@ __global__ void __launch_bounds__(kSNT) radix_hist_kernel(const HistParams p) {
     cudaGridDependencySynchronize();               // the keys may come from the previous launch
     const int lane = threadIdx.x & 31;
     const int64_t nthreads = (int64_t)gridDim.x * kSNT;
+    const int64_t gtid = blockIdx.x * (int64_t)kSNT + threadIdx.x;
     // whole warps stay converged so the votes below are legal: iterate on a warp-aligned bound
     const int64_t n_round = (p.n + 31) & ~(int64_t)31;
-    for (int64_t i = blockIdx.x * (int64_t)kSNT + threadIdx.x; i < n_round; i += 2 * nthreads) {
-        // two independent keys per trip: twice the loads in flight
-        const int64_t i2 = i + nthreads;
-        const bool valid = i < p.n, valid2 = i2 < p.n;
-        int64_t k1 = 0, k2 = 0;
-        if (valid) k1 = __ldcs(p.keys_in + i);
-        if (valid2) k2 = __ldcs(p.keys_in + i2);
-        const uint64_t P1 = pack_key(apply_rekey(k1, p.rk), p.pk);
-        const uint64_t P2 = pack_key(apply_rekey(k2, p.rk), p.pk);
-        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-        const unsigned vmask2 = __ballot_sync(0xffffffffu, valid2);
-        int pred;
-        for (int ps = 0; ps < p.npasses; ++ps) {
-            const unsigned m = (unsigned)p.bins[ps] - 1u;
-            const unsigned d = (unsigned)(P1 >> p.shift[ps]) & m;
-            const unsigned e = (unsigned)(P2 >> p.shift[ps]) & m;
-            // runs of equal digits (sorted input): one add per warp instead of a 32-way bank conflict
-            if (vmask == 0xffffffffu && __match_all_sync(0xffffffffu, d, &pred) == 0xffffffffu) {
-                if (lane == 0) atomicAdd(&h[ps * 256 + d], 32u);
-            } else if (valid) {
-                atomicAdd(&h[ps * 256 + d], 1u);
-            }
-            if (vmask2 == 0xffffffffu && __match_all_sync(0xffffffffu, e, &pred) == 0xffffffffu) {
-                if (lane == 0) atomicAdd(&h[ps * 256 + e], 32u);
-            } else if (valid2) {
-                atomicAdd(&h[ps * 256 + e], 1u);
+    for (int64_t i0 = gtid; i0 < n_round; i0 += kHistUnroll * nthreads) {
+        uint64_t P[kHistUnroll];
+        bool valid[kHistUnroll];
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; ++u) {
+            const int64_t i = i0 + u * nthreads;
+            valid[u] = i < p.n;
+            P[u] = valid[u] ? (uint64_t)__ldcs(p.keys_in + i) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; ++u) P[u] = pack_key(apply_rekey((int64_t)P[u], p.rk), p.pk);
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; ++u) {
+            if (i0 + u * nthreads - lane >= n_round) break;          // (warp-uniform) this row lies past the end
+            const bool full = __all_sync(0xffffffffu, valid[u]);
+            for (int ps = 0; ps < p.npasses; ++ps) {
+                const unsigned d = (unsigned)(P[u] >> p.shift[ps]) & ((unsigned)p.bins[ps] - 1u);
+                const unsigned d0 = __shfl_sync(0xffffffffu, d, 0);
+                if (full && __all_sync(0xffffffffu, d == d0)) {
+                    if (lane == 0) atomicAdd(&h[ps * 256 + d], 32u);
+                } else if (valid[u]) {
+                    atomicAdd(&h[ps * 256 + d], 1u);
+                }
             }
         }
     }

@@ -125,6 +125,69 @@ def test_sum_axis_long_segments(sp):
     assert_sparse_same(A.sum(axis=1), fo.sum_axis(idx, val, shape, 1), exact=False, rtol=1e-5)
 
 
+SLAB_CASES = [
+    # shape, nnz, axes: multi-tile runs of the one-pass slab kernel (csrc/slab_sum.cu)
+    ((64, 48, 40, 16), 400_000, (3, 2, 1)),          # last axis, 16-cell suffix, 640-cell suffix
+    ((300, 7, 100, 3), 200_000, (3, 2, 1)),          # nothing a power of two
+    ((1000, 1000), 600_000, (1,)),                   # rows of a matrix
+    ((50, 20000), 300_000, (1,)),                    # slabs several tiles long
+    ((2000, 3, 64), 150_000, (2, 1)),
+]
+
+
+@pytest.mark.parametrize("shape,nnz,axes", SLAB_CASES)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int32, np.int8], ids=lambda d: np.dtype(d).name)
+def test_sum_axis_slab_kernel(sp, shape, nnz, axes, dtype):
+    """The slab kernels against the oracle: skewed fill (whole regions of empty tiles, tiles far fuller than the
+    average, so several batches per tile), explicit zeros, sums that cancel to zero."""
+    from sparray_b200 import _kernels as k
+    from sparray_b200._lib import lib
+    rng = np.random.default_rng(nnz + len(shape))
+    size = int(np.prod(shape))
+    # two thirds of the elements in the first fifth of the index space, none in the second fifth
+    a = rng.integers(0, size // 5, size=2 * nnz // 3, dtype=np.int64)
+    b = rng.integers(2 * (size // 5), size, size=nnz // 3, dtype=np.int64)
+    idx = np.unique(np.concatenate([a, b]))
+    if np.dtype(dtype).kind in "iu":
+        val = rng.integers(-100, 100, size=len(idx)).astype(dtype)
+    else:
+        val = rng.standard_normal(len(idx)).astype(dtype)
+    val[::7] = 0                                     # explicit zeros are stored elements like any other
+    A = sp.FlatSparray(idx, val, shape=shape, is_canonical=True)
+    for axis in axes:
+        slab = k.slab_geometry(shape, axis)
+        assert lib.spb_axis_sum_slab_ok(len(idx), *slab) == 1, "case no longer exercises the slab kernel"
+        want = fo.sum_axis(idx, val, shape, axis)
+        new_shape = want[2]
+        cells = int(np.prod(new_shape))
+        exact = np.dtype(dtype).kind in "iu"
+        # called directly: the host's choice between this and the dense-accumulator path is a measured preference
+        oi, ov, cnt = k.axis_sum_slab(A.indices, A.data, slab, min(len(idx), cells))
+        m = int(cnt.item())
+        got = sp.FlatSparray(oi[:m], ov[:m], shape=new_shape, is_canonical=True)
+        assert got.dtype == np.float64
+        assert_sparse_same(got, want, exact=exact, rtol=RTOL.get(np.dtype(dtype), 1e-12))
+        # ... and whatever path sum() itself takes
+        assert_sparse_same(A.sum(axis=axis), want, exact=exact, rtol=RTOL.get(np.dtype(dtype), 1e-12))
+
+
+def test_sum_axis_slab_ignores_indices_past_the_shape(sp):
+    """resize() may leave flat indices >= prod(shape) behind (flat.py:185-187 only asserts prod(shape) >= nnz):
+    they must not touch anybody's accumulators."""
+    from sparray_b200 import _kernels as k
+    import torch
+    shape = (100, 50)
+    idx = np.arange(0, 6000, 3, dtype=np.int64)      # 2000 elements, 334 of them past the 5000 cells
+    val = np.ones(len(idx), dtype=np.float64)
+    ti, tv = torch.from_numpy(idx).cuda(), torch.from_numpy(val).cuda()
+    oi, ov, cnt = k.axis_sum_slab(ti, tv, k.slab_geometry(shape, 1), 100)
+    m = int(cnt.item())
+    keep = idx < 5000
+    want = np.bincount(idx[keep] // 50, minlength=100).astype(np.float64)
+    np.testing.assert_array_equal(oi[:m].cpu().numpy(), np.nonzero(want)[0])
+    np.testing.assert_array_equal(ov[:m].cpu().numpy(), want[want > 0])
+
+
 def test_config2_chain(sp):
     """BASELINE config 2 at full size: c = a*b (intersection) then c.sum(axis=2); also a.sum(axis=2)."""
     shape = (256, 256, 256, 64)
