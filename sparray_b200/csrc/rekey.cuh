@@ -20,6 +20,8 @@ struct Rekey {
     int f_in[kMaxRekeyDims];
     int f_out[kMaxRekeyDims];
     uint64_t f_mask[kMaxRekeyDims];       // (size of the group) - 1; all ones for the outermost group
+    int out32;                            // pow2 and no inner field reaches bit 32: if the largest new key is below
+                                          // 2^32 (the caller's knowledge) the fields move in 32-bit registers
 };
 
 template <int NF>
@@ -28,6 +30,29 @@ __device__ __forceinline__ int64_t move_fields(uint64_t idx, const Rekey& r) {
 #pragma unroll
     for (int f = 0; f < NF; ++f) acc |= ((idx >> r.f_in[f]) & r.f_mask[f]) << r.f_out[f];
     return (int64_t)acc;
+}
+
+// the same with the new key in one 32-bit register (Rekey::out32): half the shifts and masks
+template <int NF>
+__device__ __forceinline__ uint32_t move_fields32(uint64_t idx, const Rekey& r) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) acc |= ((uint32_t)(idx >> r.f_in[f]) & (uint32_t)r.f_mask[f]) << r.f_out[f];
+    return acc;
+}
+
+__device__ __forceinline__ uint32_t apply_rekey32(int64_t idx, const Rekey& r) {
+    switch (r.nfields) {
+        case 0: return 0;
+        case 1: return move_fields32<1>((uint64_t)idx, r);
+        case 2: return move_fields32<2>((uint64_t)idx, r);
+        case 3: return move_fields32<3>((uint64_t)idx, r);
+        case 4: return move_fields32<4>((uint64_t)idx, r);
+        default: break;
+    }
+    uint32_t acc = 0;
+    for (int f = 0; f < r.nfields; ++f) acc |= ((uint32_t)((uint64_t)idx >> r.f_in[f]) & (uint32_t)r.f_mask[f]) << r.f_out[f];
+    return acc;
 }
 
 // NDIM known at compile time: straight-line code, no per-axis predicates
@@ -95,6 +120,7 @@ inline int make_rekey(Rekey& rk, int ndim, const int64_t* in_strides, const int6
     }
     if (ndim && in_strides[ndim - 1] != 1) return SPB_ERR_BAD_ARG;
     if (rk.pow2) {
+        rk.out32 = ndim > 0;
         for (int ax = 0; ax < ndim; ++ax) {
             const uint64_t m = (uint64_t)out_strides[ax];
             if (!m) continue;                     // dropped group
@@ -104,6 +130,9 @@ inline int make_rekey(Rekey& rk, int ndim, const int64_t* in_strides, const int6
             rk.f_in[f] = (int)rk.in_div[ax].shift;
             rk.f_out[f] = s;
             rk.f_mask[f] = ax == 0 ? ~0ull : (uint64_t)(in_strides[ax - 1] / in_strides[ax]) - 1;
+            // (the outermost group has no size here -- its mask is all ones: the caller must know that the
+            // largest new key is below 2^32 before it moves the fields in 32 bits)
+            if (s >= 32 || (ax != 0 && (rk.f_mask[f] << s) >= (1ull << 32))) rk.out32 = 0;
         }
     }
     return SPB_OK;

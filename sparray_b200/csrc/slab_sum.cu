@@ -43,7 +43,7 @@ constexpr int kSlabNT = 256;
 constexpr int kSlabItems = 8;                  // consecutive elements per thread
 constexpr int kSlabBatch = kSlabNT * kSlabItems;
 constexpr int kSlabCapCells = 4096;            // output cells a tile may span: 32 KB of float64 accumulators
-constexpr int kSlabTileElems = 2048;           // stored elements per tile, on average
+constexpr int kSlabTileElems = 1792;           // stored elements per tile, on average: nearly every tile fits ONE batch
 constexpr int kSlabCtasPerSm = 5;              // ~45 KB of shared memory each
 constexpr int64_t kSlabMaxGroups = 1024;       // group counters a CTA sums to find its output offset
 

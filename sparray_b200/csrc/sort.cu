@@ -63,6 +63,7 @@ struct HistParams {
     int shift[kMaxPasses];      // bit position of the pass's digit inside P
     int bins[kMaxPasses];
     uint64_t* hist;             // [kMaxPasses][256] counts (zeroed by the caller)
+    int p32;                    // packed keys are re-keyed in 32-bit registers (power-of-two shape, < 2^32 cells)
 };
 
 // ---- all digit histograms in one read --------------------------------------------------------
@@ -71,44 +72,55 @@ struct HistParams {
 // bank conflict.
 constexpr int kHistUnroll = 4;
 
+// NP passes known at compile time (0: any number): the digit loop is straight-line code
+template <int NP, bool P32>
 __global__ void __launch_bounds__(kSNT) radix_hist_kernel(const HistParams p) {
     __shared__ unsigned h[kMaxPasses * 256];
-    for (int i = threadIdx.x; i < p.npasses * 256; i += kSNT) h[i] = 0;
+    const int npasses = NP ? NP : p.npasses;
+    for (int i = threadIdx.x; i < npasses * 256; i += kSNT) h[i] = 0;
     __syncthreads();
     cudaGridDependencySynchronize();               // the keys may come from the previous launch
+    using PT = typename std::conditional<P32, uint32_t, uint64_t>::type;
     const int lane = threadIdx.x & 31;
     const int64_t nthreads = (int64_t)gridDim.x * kSNT;
     const int64_t gtid = blockIdx.x * (int64_t)kSNT + threadIdx.x;
     // whole warps stay converged so the votes below are legal: iterate on a warp-aligned bound
     const int64_t n_round = (p.n + 31) & ~(int64_t)31;
     for (int64_t i0 = gtid; i0 < n_round; i0 += kHistUnroll * nthreads) {
-        uint64_t P[kHistUnroll];
+        int64_t raw[kHistUnroll];
+        PT P[kHistUnroll];
         bool valid[kHistUnroll];
 #pragma unroll
         for (int u = 0; u < kHistUnroll; ++u) {
             const int64_t i = i0 + u * nthreads;
             valid[u] = i < p.n;
-            P[u] = valid[u] ? (uint64_t)__ldcs(p.keys_in + i) : 0;
+            raw[u] = valid[u] ? __ldcs(p.keys_in + i) : 0;
         }
 #pragma unroll
-        for (int u = 0; u < kHistUnroll; ++u) P[u] = pack_key(apply_rekey((int64_t)P[u], p.rk), p.pk);
+        for (int u = 0; u < kHistUnroll; ++u) {
+            if constexpr (P32) P[u] = apply_rekey32(raw[u], p.rk);
+            else P[u] = pack_key(apply_rekey(raw[u], p.rk), p.pk);
+        }
 #pragma unroll
         for (int u = 0; u < kHistUnroll; ++u) {
             if (i0 + u * nthreads - lane >= n_round) break;          // (warp-uniform) this row lies past the end
             const bool full = __all_sync(0xffffffffu, valid[u]);
-            for (int ps = 0; ps < p.npasses; ++ps) {
-                const unsigned d = (unsigned)(P[u] >> p.shift[ps]) & ((unsigned)p.bins[ps] - 1u);
-                const unsigned d0 = __shfl_sync(0xffffffffu, d, 0);
-                if (full && __all_sync(0xffffffffu, d == d0)) {
-                    if (lane == 0) atomicAdd(&h[ps * 256 + d], 32u);
-                } else if (valid[u]) {
-                    atomicAdd(&h[ps * 256 + d], 1u);
+#pragma unroll
+            for (int ps = 0; ps < (NP ? NP : kMaxPasses); ++ps) {
+                if (ps < npasses) {
+                    const unsigned d = (unsigned)(P[u] >> p.shift[ps]) & ((unsigned)p.bins[ps] - 1u);
+                    const unsigned d0 = __shfl_sync(0xffffffffu, d, 0);
+                    if (full && __all_sync(0xffffffffu, d == d0)) {
+                        if (lane == 0) atomicAdd(&h[ps * 256 + d], 32u);
+                    } else if (valid[u]) {
+                        atomicAdd(&h[ps * 256 + d], 1u);
+                    }
                 }
             }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < p.npasses * 256; i += kSNT)
+    for (int i = threadIdx.x; i < npasses * 256; i += kSNT)
         if (h[i]) atomicAdd(reinterpret_cast<unsigned long long*>(p.hist) + i, (unsigned long long)h[i]);
 }
 
@@ -171,6 +183,7 @@ struct PassParams {
     uint64_t* state;            // [ntiles][bins] look-back words
     uint32_t epoch;
     int vals_aligned;           // vals_in is 16-byte aligned: full tiles are fetched by TMA
+    int p32;                    // FIRST: re-key in 32-bit registers (see run_sort)
 };
 
 template <int VB> struct ValType;
@@ -311,6 +324,14 @@ __global__ void __launch_bounds__(kSNT, PassCfg<K32, VB>::kMinCtas) radix_pass_k
         if (e < items) {
             if constexpr (FIRST) {
                 const int64_t raw = __ldcs(reinterpret_cast<const int64_t*>(p.keys_in) + base + e);
+                if constexpr (K32) {
+                    if (p.p32) {                   // (uniform) P == new key < 2^32, nothing squeezed
+                        const uint32_t P32 = apply_rekey32(raw, p.rk);
+                        dr[k] = (P32 >> p.in_shift) & dmask;
+                        key[k] = (KS)P32;
+                        continue;
+                    }
+                }
                 const uint64_t P = pack_key(apply_rekey(raw, p.rk), p.pk);
                 dr[k] = (unsigned)(P >> p.in_shift) & dmask;
                 if (!LAST && p.squeeze) {
@@ -627,7 +648,23 @@ int run_sort(const int64_t* idx, const void* val, int64_t n, const Rekey& rk, ui
     int64_t hblocks = ceil_div(n, kSNT * 16);
     const int64_t hcap = (int64_t)device_sm_count() * 8;
     if (hblocks > hcap) hblocks = hcap;
-    SPB_CUDA_TRY(launch_pdl(radix_hist_kernel, dim3((unsigned)hblocks), dim3(kSNT), 0, stream, hp));
+    // power-of-two shape whose new keys fit 32 bits: the re-key runs in 32-bit registers
+    const bool p32 = rk.ndim > 0 && rk.pow2 && rk.out32 && pk.pow2 && pl.total_bits <= 32;
+    hp.p32 = p32;
+    {
+        const dim3 hg((unsigned)hblocks), hb(kSNT);
+        cudaError_t e;
+        if (p32 && np == 1) e = launch_pdl(radix_hist_kernel<1, true>, hg, hb, 0, stream, hp);
+        else if (p32 && np == 2) e = launch_pdl(radix_hist_kernel<2, true>, hg, hb, 0, stream, hp);
+        else if (p32 && np == 3) e = launch_pdl(radix_hist_kernel<3, true>, hg, hb, 0, stream, hp);
+        else if (p32 && np == 4) e = launch_pdl(radix_hist_kernel<4, true>, hg, hb, 0, stream, hp);
+        else if (np == 1) e = launch_pdl(radix_hist_kernel<1, false>, hg, hb, 0, stream, hp);
+        else if (np == 2) e = launch_pdl(radix_hist_kernel<2, false>, hg, hb, 0, stream, hp);
+        else if (np == 3) e = launch_pdl(radix_hist_kernel<3, false>, hg, hb, 0, stream, hp);
+        else if (np == 4) e = launch_pdl(radix_hist_kernel<4, false>, hg, hb, 0, stream, hp);
+        else e = launch_pdl(radix_hist_kernel<0, false>, hg, hb, 0, stream, hp);
+        SPB_CUDA_TRY(e);
+    }
     SPB_LAUNCHED(1);
     SPB_CUDA_TRY(launch_pdl(radix_scan_kernel, dim3((unsigned)np), dim3(256), 0, stream, hist));
     SPB_LAUNCHED(1);
@@ -637,6 +674,7 @@ int run_sort(const int64_t* idx, const void* val, int64_t n, const Rekey& rk, ui
     PassParams p{};
     p.n = n; p.rk = rk; p.pk = pk; p.state = ws_state(ws);
     p.squeeze = pl.mode == MODE_SQUEEZE;
+    p.p32 = p32 && !p.squeeze;
     p.sq_width = pl.sq_width;
     const void* kin = idx;
     const void* vin = val;
