@@ -34,8 +34,8 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
                                                               const int64_t clear_n) {
     cudaTriggerProgrammaticLaunchCompletion();
     cudaGridDependencySynchronize();   // operands (and n_dev) may come from the previous launch
-    // the look-back words of the emitting pass that follows start from zero (it waits for this whole grid):
-    // no memset node in front of it when the chain is captured into a CUDA graph
+    // the group counters of the emitting launches that follow start from zero (they wait for this whole grid):
+    // no memset node in front of them when the chain is captured into a CUDA graph
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < clear_n; i += (int64_t)gridDim.x * blockDim.x)
         clear_state[i] = 0;
     if (n_dev) {                       // the producer's count never left the device; n is its upper bound
@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(256) axis_accumulate_runs_kernel(const int64_t
                                                               const int64_t clear_n) {
     cudaTriggerProgrammaticLaunchCompletion();
     cudaGridDependencySynchronize();   // operands (and n_dev) may come from the previous launch
-    // the look-back words of the emitting pass that follows start from zero (it waits for this whole grid):
-    // no memset node in front of it when the chain is captured into a CUDA graph
+    // the group counters of the emitting launches that follow start from zero (they wait for this whole grid):
+    // no memset node in front of them when the chain is captured into a CUDA graph
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < clear_n; i += (int64_t)gridDim.x * blockDim.x)
         clear_state[i] = 0;
     if (n_dev) {                       // the producer's count never left the device; n is its upper bound
@@ -195,38 +195,96 @@ __global__ void __launch_bounds__(256) axis_accumulate_runs_kernel(const int64_t
 // Emits the touched cells in key order and puts every cell it emitted back to zero, so the
 // accumulator slab is all-zero again when the call is over (no memset per call).  One thread owns
 // kSelCells cells (one 16-byte load of flag bytes); a tile of 256 threads covers 4 K cells -- thousands of
-// tiles for the BASELINE shapes, enough to fill the machine -- and the whole block looks back (256
-// predecessor tiles per round), so the chain of tile offsets stays a round or two long.
+// tiles for the BASELINE shapes, enough to fill the machine.
+// Two launches: count_touched_kernel reads the flags only and leaves one count per tile plus one per group of
+// 64 tiles; select_touched_kernel then works out its output offset on its own (a few dozen L2 loads) -- no CTA
+// waits for another.  (With a decoupled look-back in a single pass the tiles ran in lockstep waves, each one
+// waiting for the slowest predecessor's count: 160 us for the 16.7 M cells of a config-2 axis-0 sum, against
+// the ~60 us its traffic takes.)
 constexpr int kSelCells = 16;
+constexpr int kSelGroupShift = 6;          // tiles per group counter: 64
+
+struct SelCounts {
+    unsigned long long* group_cnt;         // [ceil(ntiles / 64)], zero before count_touched_kernel runs
+    int* counts;                           // [ntiles]
+};
+
+__device__ __forceinline__ unsigned touched_bits(const uint8_t* touched, int64_t first, int64_t cells) {
+    unsigned bits = 0;
+    if (first < cells) {               // the flag array is padded to a multiple of 64 (the padding stays zero)
+        const uint4 raw = *reinterpret_cast<const uint4*>(touched + first);
+        const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bits |= (((w[k] & 0x01010101u) * 0x01020408u) >> 24) << (4 * k);
+    }
+    return bits;
+}
+
+__global__ void __launch_bounds__(256) count_touched_kernel(const uint8_t* __restrict__ touched, int64_t cells,
+                                                            const SelCounts sc) {
+    __shared__ int s_w[8];
+    const int64_t tile = blockIdx.x;
+    const int64_t first = (tile * 256 + threadIdx.x) * kSelCells;
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();   // flags (and the zeroed group counters) come from the previous launch
+    int cnt = __popc(touched_bits(touched, first, cells));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) total += s_w[w];
+        sc.counts[tile] = total;
+        if (total) atomicAdd(sc.group_cnt + (tile >> kSelGroupShift), (unsigned long long)total);
+    }
+}
 
 __global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict__ acc, uint8_t* __restrict__ touched,
                                                              int64_t cells, int64_t key_base, int64_t* __restrict__ out_idx,
                                                              double* __restrict__ out_val, int64_t* out_count,
-                                                             uint64_t* state, uint32_t epoch) {
+                                                             const SelCounts sc) {
+    __shared__ int64_t s_red[8];
+    __shared__ int s_w[8];
     const int64_t tile = blockIdx.x;
-    const int64_t first = (tile * 256 + threadIdx.x) * kSelCells;
-    cudaGridDependencySynchronize();   // accumulators come from the previous launch
-    unsigned bits = 0;
-    if (first < cells) {               // the flag array is padded to a multiple of 64 (the padding stays zero)
-        uint4* const flags = reinterpret_cast<uint4*>(touched + first);
-        const uint4 raw = *flags;
-        const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-        for (int k = 0; k < 16; ++k) bits |= ((w[k >> 2] >> (8 * (k & 3))) & 1u) << k;
-        if (bits) *flags = make_uint4(0, 0, 0, 0);
-    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t first = (tile * 256 + tid) * kSelCells;
+    cudaGridDependencySynchronize();   // accumulators and counts come from the previous launches
+    const unsigned bits = touched_bits(touched, first, cells);
+    if (bits) *reinterpret_cast<uint4*>(touched + first) = make_uint4(0, 0, 0, 0);
     const int cnt = __popc(bits);
-    const int64_t off = compact_offset_256<true>(cnt, state, epoch, tile, tile == gridDim.x - 1, out_count);
-    // Warp-cooperative emission: the warp's outputs are one contiguous run, written 32 at a time (coalesced
-    // whether the cells are nearly all touched or nearly all empty).  Output r of the warp belongs to the
-    // first lane whose inclusive count exceeds r, and is that lane's (r - exclusive count)-th set bit.
-    const int lane = threadIdx.x & 31;
+    // output offset of the tile: the groups in front of its own + the earlier tiles of its own group
+    int64_t gsum = 0;
+    {
+        const int64_t g = tile >> kSelGroupShift;
+        for (int64_t j = tid; j < g; j += 256) gsum += (int64_t)__ldg(sc.group_cnt + j);
+        for (int64_t j = (g << kSelGroupShift) + tid; j < tile; j += 256) gsum += __ldg(sc.counts + j);
+    }
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+    if (lane == 31) s_w[warp] = incl;
+    if (lane == 0) s_red[warp] = gsum;
+    __syncthreads();
+    int64_t tile_base = 0;
+    int wofs = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        tile_base += s_red[w];
+        if (w < warp) wofs += s_w[w];
+        tile_total += s_w[w];
+    }
+    if (tile == gridDim.x - 1 && tid == 0) *out_count = tile_base + tile_total;
+    const int64_t off = tile_base + wofs + incl - cnt;
+    // Warp-cooperative emission: the warp's outputs are one contiguous run, written 32 at a time (coalesced
+    // whether the cells are nearly all touched or nearly all empty).  Output r of the warp belongs to the
+    // first lane whose inclusive count exceeds r, and is that lane's (r - exclusive count)-th set bit.
     const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
     const int64_t warp_off = __shfl_sync(0xffffffffu, off, 0);
     const int64_t warp_first = first - (int64_t)lane * kSelCells;
@@ -292,20 +350,28 @@ static int launch_accumulate(int dtype, const int64_t* idx, const void* val, int
 // cells of [0, cells) relative to acc / touched (touched readable up to the next multiple of 64)
 static int64_t select_tiles(int64_t cells) { return ceil_div(cells, 256 * kSelCells); }
 
-// precleared: the producer launch wiped the look-back words of this one (see the accumulate kernels)
+// Scratch of the two emitting launches, in the workspace's state region: [group counters u64][tile counts i32]
+// (small integers there can never pass for a look-back word of a live epoch: their status bits are zero).
+static int64_t select_groups(int64_t ntiles) { return ceil_div(ntiles, (int64_t)1 << kSelGroupShift); }
+static size_t select_scratch_bytes(int64_t ntiles) { return (size_t)select_groups(ntiles) * 8 + (size_t)ntiles * 4; }
+
+// precleared: the producer launch zeroed the group counters (see the accumulate kernels)
 static int launch_select(double* acc, uint8_t* touched, int64_t cells, int64_t key_base, int64_t* out_idx,
                          double* out_sums, int64_t* out_count, spb_workspace* ws, cudaStream_t stream,
                          bool precleared = false) {
     const int64_t ntiles = select_tiles(cells);
     if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
-    int rc = workspace_reserve(ws, (size_t)ntiles * 8, stream);
+    int rc = workspace_reserve(ws, select_scratch_bytes(ntiles), stream);
     if (rc) return rc;
-    uint32_t epoch;
-    rc = workspace_next_epoch(ws, stream, &epoch, !precleared);
-    if (rc) return rc;
+    SelCounts sc;
+    sc.group_cnt = reinterpret_cast<unsigned long long*>(ws_state(ws));
+    sc.counts = reinterpret_cast<int*>(sc.group_cnt + select_groups(ntiles));
+    if (!precleared) SPB_CUDA_TRY(cudaMemsetAsync(sc.group_cnt, 0, (size_t)select_groups(ntiles) * 8, stream));
+    SPB_CUDA_TRY(launch_pdl(count_touched_kernel, dim3((unsigned)ntiles), dim3(256), 0, stream,
+                            (const uint8_t*)touched, cells, sc));
     SPB_CUDA_TRY(launch_pdl(select_touched_kernel, dim3((unsigned)ntiles), dim3(256), 0, stream, acc, touched, cells,
-                            key_base, out_idx, out_sums, out_count, ws_state(ws), epoch));
-    SPB_LAUNCHED(1);
+                            key_base, out_idx, out_sums, out_count, sc));
+    SPB_LAUNCHED(2);
     return (int)cudaGetLastError();
 }
 
@@ -341,9 +407,10 @@ static int axis_sum_window(int dtype, const int64_t* idx, const void* val, int64
     ws->accum_dirty = 1;
     const int64_t ntiles = select_tiles(cells);
     if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
-    rc = workspace_reserve(ws, (size_t)ntiles * 8, stream);      // the emitting pass's look-back words, wiped by the
-    if (rc) return rc;                                           // accumulate launch
-    rc = launch_accumulate(dtype, idx, val, n, n_dev, rk, cell_lo, cells, acc, touched, ws_state(ws), ntiles, stream);
+    rc = workspace_reserve(ws, select_scratch_bytes(ntiles), stream);    // the emitting launches' counters: the group
+    if (rc) return rc;                                                   // counters are zeroed by the accumulate launch
+    rc = launch_accumulate(dtype, idx, val, n, n_dev, rk, cell_lo, cells, acc, touched, ws_state(ws),
+                           select_groups(ntiles), stream);
     if (rc) return rc;
     rc = launch_select(acc, touched, cells, cell_lo, out_idx, out_sums, out_count, ws, stream, true);
     if (rc == SPB_OK) ws->accum_dirty = 0;
