@@ -6,15 +6,21 @@ import os
 
 import numpy as np
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN = os.path.join(_DIR, "golden_v1.npz")
+GOLDEN_F = os.path.join(_DIR, "golden_f_v1.npz")      # make_golden_f.py
 _CACHE = {}
 
 
 def load():
     if "z" not in _CACHE:
-        z = np.load(GOLDEN)
-        _CACHE["z"] = {k: z[k] for k in z.files}
-        _CACHE["manifest"] = json.loads(str(_CACHE["z"]["manifest"]))
+        arrays, manifest = {}, []
+        for path in (GOLDEN, GOLDEN_F):
+            z = np.load(path)
+            arrays.update({k: z[k] for k in z.files if k != "manifest"})
+            manifest += json.loads(str(z["manifest"]))
+        _CACHE["z"] = arrays
+        _CACHE["manifest"] = manifest
     return _CACHE["manifest"], _CACHE["z"]
 
 
@@ -58,6 +64,22 @@ def run_case(case, cls, seam=None):
     if op == "seam_len_range":
         return {"len": np.asarray([seam.len_range(*map(int, t)) for t in inp["args"]], dtype=np.int64)}
     shape = tuple(prm["shape"])
+    if op == "prog":
+        # a small program over the public API (tests/golden/make_golden_f.py)
+        env = {"np": np, "FlatSparray": cls, "a": cls(inp["a_indices"], inp["a_data"], shape=shape, is_canonical=True)}
+        if "b_indices" in inp:
+            env["b"] = cls(inp["b_indices"], inp["b_data"], shape=tuple(prm["b_shape"]), is_canonical=True)
+        for k, v in inp.items():
+            if k not in ("a_indices", "a_data", "b_indices", "b_data"):
+                env[k] = np.array(v, copy=True)
+        for st in prm["setup"]:
+            exec(st, env)
+        r = eval(prm["result"], env)
+        if hasattr(r, "indices") and hasattr(r, "shape") and not isinstance(r, np.ndarray) and not hasattr(r, "detach"):
+            return sp_out("", r)
+        if hasattr(r, "tocoo") and not hasattr(r, "indices"):
+            r = r.toarray()
+        return {"dense": to_np(r)}
     if op == "binop":
         a = cls(inp["a_indices"], inp["a_data"], shape=shape, is_canonical=True)
         b = cls(inp["b_indices"], inp["b_data"], shape=shape, is_canonical=True)
@@ -104,6 +126,9 @@ def check_case(case, got, rtol_f64=1e-12, rtol_f32=1e-5):
         want = dict(want, indices=want["indices"][order], data=want["data"][order])
     exact = case["op"] in ("seam_merge", "seam_combine_ranges", "seam_len_range", "binop",
                            "transpose", "getitem", "ctor")
+    if case["op"] == "prog":
+        # everything but the contractions is data movement or one elementwise op: bit-exact
+        exact = ".dot(" not in case["params"]["result"]
     for k, w in want.items():
         if k not in got:
             if case["op"] in ("dot_vec", "dot_1d") and k != "dense":

@@ -28,6 +28,12 @@ def test_golden(sp, case):
     gr.check_case(case, gr.run_case(case, sp.FlatSparray))
 
 
+@pytest.mark.parametrize("case", gr.cases("prog"), ids=lambda c: c["name"])
+def test_golden_f_rows(sp, case):
+    """SURVEY.md section 8(f) rows against outputs of the reference itself (tests/golden/make_golden_f.py)."""
+    gr.check_case(case, gr.run_case(case, sp.FlatSparray))
+
+
 SHAPES = [((300, 500), 40000), ((37, 41, 43), 30000), ((16, 8, 32, 12), 25000), ((64, 64, 64, 16), 300000),
           ((5, 1, 7, 1, 9), 200), ((2 ** 20, 2 ** 18), 100000)]
 
@@ -498,6 +504,25 @@ def test_config4_full_size_properties(sp):
     del D
     Q = W * W
     assert Q.nnz == n and bool((Q.indices == idx).all().item()) and bool((Q.data == val * val).all().item())
+
+
+def test_config4_downscale_vs_oracle(sp):
+    """BASELINE config[3] (2-D float64, dot with a dense vector and sum(axis=1)) at a tenth of its stated size --
+    10^7 stored elements, 2-D and row-sparse like the original (316228 x 316228) -- with NON-integer data,
+    against the oracle's restatement of flat.py:538-568 / :607-626 (the full size is property-checked only:
+    test_config4_full_size_properties).  Tolerance: 1e-12 relative (north_star, float64)."""
+    rng = np.random.default_rng(44)
+    shape = (316_228, 316_228)
+    nnz = 10_000_000
+    idx = np.unique(rng.integers(0, shape[0] * shape[1], size=nnz, dtype=np.int64))
+    val = rng.standard_normal(len(idx))
+    x = rng.standard_normal(shape[1])
+    A = sp.FlatSparray(idx, val, shape=shape, is_canonical=True)
+    want = fo.dot_dense_vector(idx, val, shape, x)
+    got = to_np(A.dot(x))
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12 * np.abs(want).max())
+    assert_sparse_same(A.sum(axis=1), fo.sum_axis(idx, val, shape, 1), exact=False, rtol=1e-12)
+    assert_sparse_same(A.sum(axis=0), fo.sum_axis(idx, val, shape, 0), exact=False, rtol=1e-12)
 
 
 def test_axis_accumulate_and_emit_ranges(sp):

@@ -59,7 +59,9 @@ def test_kat_len_range():            # test_compat.py:48-53
         assert fo.len_range(*t) == len(range(*t))
 
 
-@pytest.mark.parametrize("case", gr.cases(), ids=lambda c: c["name"])
+# (the "prog" cases -- SURVEY.md section 8(f) rows -- are outputs of the reference that the PRODUCT is held to
+# directly, tests/test_gpu_ops.py::test_golden_f_rows; the oracle restates the section 8(a) path only)
+@pytest.mark.parametrize("case", [c for c in gr.cases() if c["op"] != "prog"], ids=lambda c: c["name"])
 def test_golden(case):
     got = gr.run_case(case, fo.OracleSparray, OracleSeam)
     gr.check_case(case, got)
