@@ -4,12 +4,24 @@
 // whenever the reduced array is small enough to hold densely.
 #include "rekey.cuh"
 
+#include <string.h>
+
 // ---- axis sums into a dense accumulator (no sort) ---------------------------------------------------
 // When the reduced array prod(new_shape) is small enough to hold densely, sum(axis != last)
 // (flat.py:617-625) does not need the re-key + radix sort at all: every stored element adds its
 // value into acc[new_key] with a float64 atomic (the accumulator is L2-resident for the BASELINE
-// configs), marks the cell as touched (explicit zeros must survive, so "sum == 0" cannot be the
-// test), and one compaction pass over the cells emits the touched ones in key order.
+// configs), and one compaction pass over the cells emits the touched ones in key order.
+//
+// "Touched" cannot be "sum != 0": explicit zeros are stored elements and must survive (and so must sums
+// that cancel).  Two ways to tell:
+//   * flags   -- one byte per cell, set next to every atomic.  The emitting pass then scans 1 byte per cell:
+//     the right thing when few cells are touched (a lazily counted product: 10^5 elements into 4 M cells).
+//   * sentinel -- no flags at all.  Between calls every accumulator holds -0.0.  IEEE 754 round-to-nearest:
+//     x + (-0.0) == x for every x but -0.0 itself, and sums that cancel give +0.0, never -0.0; stored -0.0
+//     values are turned into +0.0 on the way in (np.bincount starts from +0.0, so it also yields +0.0 for
+//     them).  A cell is untouched iff it still holds the bit pattern of -0.0.  This saves one scattered store
+//     per element: with a middle or leading axis reduced, a warp's 32 elements hit 32 different sectors, and
+//     the flag stores were 45 % of the accumulate pass (190 -> 125 us for a config-2 axis-0 sum).
 namespace spb {
 
 // A warp reads 32 consecutive elements (coalesced), re-keys them, combines runs of equal new keys with a
@@ -25,7 +37,11 @@ __device__ __forceinline__ int64_t window_cell(int64_t idx, const Rekey& rk, int
     return (uint64_t)c < (uint64_t)cells ? c : -1;
 }
 
-template <typename T>
+// RUNS: the finest axis group is reduced, so neighbouring elements can fall into the same cell; otherwise they
+// never do (distinct flat indices that agree on every kept coordinate differ in a coarser, reduced one and lie
+// far apart) and the run detection -- two shuffles and a vote per element on a kernel that is bound by its
+// memory-instruction queue -- is left out
+template <typename T, bool RUNS>
 __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
                                                               int64_t n, const int64_t* __restrict__ n_dev,
                                                               const Rekey rk, double* __restrict__ acc,
@@ -51,8 +67,8 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
         if (gtid < n) {
             const int64_t key = window_cell(__ldcs(idx + gtid), rk, cell_lo, cells);
             if (key >= 0) {
-                atomicAdd(acc + key, (double)__ldcs(val + gtid));
-                touched[key] = 1;
+                atomicAdd(acc + key, (double)__ldcs(val + gtid) + 0.0);      // (-0.0 goes in as +0.0)
+                if (touched) touched[key] = 1;
             }
         }
         return;
@@ -67,11 +83,21 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
         for (int u = 0; u < kAccUnroll; ++u) {
             const int64_t i = base + u * 32 + lane;
             key[u] = i < n ? __ldcs(idx + i) : -1;
-            v[u] = i < n ? (double)__ldcs(val + i) : 0.0;
+            v[u] = i < n ? (double)__ldcs(val + i) + 0.0 : 0.0;              // (-0.0 goes in as +0.0)
         }
 #pragma unroll
         for (int u = 0; u < kAccUnroll; ++u)
             if (key[u] >= 0) key[u] = window_cell(key[u], rk, cell_lo, cells);
+        if constexpr (!RUNS) {
+#pragma unroll
+            for (int u = 0; u < kAccUnroll; ++u) {
+                if (key[u] >= 0) {
+                    atomicAdd(acc + key[u], v[u]);
+                    if (touched) touched[key[u]] = 1;  // (sentinel mode: no flags)
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (int u = 0; u < kAccUnroll; ++u) {
             // runs = maximal stretches of ADJACENT lanes with the same key (equal keys further apart are
@@ -90,7 +116,7 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
             const bool last = lane == 31 || ((heads >> (lane + 1)) & 1u);
             if (key[u] >= 0 && last) {
                 atomicAdd(acc + key[u], s);
-                touched[key[u]] = 1;               // a flag per cell: explicit zeros survive
+                if (touched) touched[key[u]] = 1;  // a flag per cell: explicit zeros survive
             }
         }
     }
@@ -148,7 +174,7 @@ __global__ void __launch_bounds__(256) axis_accumulate_runs_kernel(const int64_t
 #pragma unroll
         for (int j = 0; j < kAccItems; ++j) {
             key[j] = i0 + j < n ? __ldcs(idx + i0 + j) : -1;
-            v[j] = i0 + j < n ? (double)__ldcs(val + i0 + j) : 0.0;
+            v[j] = i0 + j < n ? (double)__ldcs(val + i0 + j) + 0.0 : 0.0;    // (-0.0 goes in as +0.0)
         }
 #pragma unroll
         for (int j = 0; j < kAccItems; ++j)
@@ -169,7 +195,7 @@ __global__ void __launch_bounds__(256) axis_accumulate_runs_kernel(const int64_t
                     if (key[j] != run) {
                         if (run >= 0) {
                             atomicAdd(acc + run, rs);
-                            touched[run] = 1;
+                            if (touched) touched[run] = 1;
                         }
                         run = key[j];
                         rs = v[j];
@@ -180,14 +206,14 @@ __global__ void __launch_bounds__(256) axis_accumulate_runs_kernel(const int64_t
             }
             if (run >= 0) {
                 atomicAdd(acc + run, rs);
-                touched[run] = 1;       // a flag per cell: explicit zeros survive
+                if (touched) touched[run] = 1;       // a flag per cell: explicit zeros survive
             }
         }
         bool last;
         s = warp_run_sum(cell, s, lane, last);
         if (cell >= 0 && last) {
             atomicAdd(acc + cell, s);
-            touched[cell] = 1;
+            if (touched) touched[cell] = 1;
         }
     }
 }
@@ -220,14 +246,31 @@ __device__ __forceinline__ unsigned touched_bits(const uint8_t* touched, int64_t
     return bits;
 }
 
-__global__ void __launch_bounds__(256) count_touched_kernel(const uint8_t* __restrict__ touched, int64_t cells,
+// sentinel mode: a cell is touched iff it no longer holds the bit pattern of -0.0 (acc is readable, and clean,
+// up to the next multiple of 16 cells)
+__device__ __forceinline__ unsigned sentinel_bits(const double* acc, int64_t first, int64_t cells) {
+    unsigned bits = 0;
+    if (first < cells) {
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(acc + first);
+#pragma unroll
+        for (int k = 0; k < kSelCells / 2; ++k) {
+            const ulonglong2 w = p[k];
+            bits |= (unsigned)(w.x != kNegZeroBits) << (2 * k);
+            bits |= (unsigned)(w.y != kNegZeroBits) << (2 * k + 1);
+        }
+    }
+    return bits;
+}
+
+__global__ void __launch_bounds__(256) count_touched_kernel(const double* __restrict__ acc,
+                                                            const uint8_t* __restrict__ touched, int64_t cells,
                                                             const SelCounts sc) {
     __shared__ int s_w[8];
     const int64_t tile = blockIdx.x;
     const int64_t first = (tile * 256 + threadIdx.x) * kSelCells;
     cudaTriggerProgrammaticLaunchCompletion();
     cudaGridDependencySynchronize();   // flags (and the zeroed group counters) come from the previous launch
-    int cnt = __popc(touched_bits(touched, first, cells));
+    int cnt = __popc(touched ? touched_bits(touched, first, cells) : sentinel_bits(acc, first, cells));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
@@ -244,15 +287,20 @@ __global__ void __launch_bounds__(256) count_touched_kernel(const uint8_t* __res
 __global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict__ acc, uint8_t* __restrict__ touched,
                                                              int64_t cells, int64_t key_base, int64_t* __restrict__ out_idx,
                                                              double* __restrict__ out_val, int64_t* out_count,
-                                                             const SelCounts sc) {
+                                                             const SelCounts sc, const double clean) {
     __shared__ int64_t s_red[8];
     __shared__ int s_w[8];
     const int64_t tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t first = (tile * 256 + tid) * kSelCells;
     cudaGridDependencySynchronize();   // accumulators and counts come from the previous launches
-    const unsigned bits = touched_bits(touched, first, cells);
-    if (bits) *reinterpret_cast<uint4*>(touched + first) = make_uint4(0, 0, 0, 0);
+    unsigned bits;
+    if (touched) {
+        bits = touched_bits(touched, first, cells);
+        if (bits) *reinterpret_cast<uint4*>(touched + first) = make_uint4(0, 0, 0, 0);
+    } else {
+        bits = sentinel_bits(acc, first, cells);
+    }
     const int cnt = __popc(bits);
     // output offset of the tile: the groups in front of its own + the earlier tiles of its own group
     int64_t gsum = 0;
@@ -306,7 +354,7 @@ __global__ void __launch_bounds__(256) select_touched_kernel(double* __restrict_
             // one gather per emitted element (measured against loading every cell of a touched thread up
             // front and emitting from shared memory: 111 vs 126 us on the config-2 operand)
             out_val[warp_off + r] = acc[warp_first + local];
-            acc[warp_first + local] = 0.0;
+            acc[warp_first + local] = clean;       // -0.0 (the workspace's slab) or +0.0 (caller-owned buffers)
         }
     }
 }
@@ -322,13 +370,17 @@ static int launch_accumulate(int dtype, const int64_t* idx, const void* val, int
     if (blocks > (int64_t)device_sm_count() * 16) blocks = (int64_t)device_sm_count() * 16;
     // long contiguous runs (innermost axis reduced, >= 8 elements per output cell on average): the variant
     // that pre-reduces inside a lane and scans once per 128 elements
-    const bool long_runs = rk.ndim >= 1 && rk.out_mul[rk.ndim - 1] == 0 && n >= 8 * cells;
+    const bool runs = rk.ndim >= 1 && rk.out_mul[rk.ndim - 1] == 0;      // the finest axis group is reduced
+    const bool long_runs = runs && n >= 8 * cells;
 #define SPB_ACC(T)                                                                                            \
     if (long_runs) {                                                                                          \
         SPB_CUDA_TRY(launch_pdl(axis_accumulate_runs_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, \
                                 idx, (const T*)val, n, n_dev, rk, acc, touched, cell_lo, cells, clear_state, clear_n)); \
+    } else if (runs) {                                                                                        \
+        SPB_CUDA_TRY(launch_pdl(axis_accumulate_kernel<T, true>, dim3((unsigned)blocks), dim3(256), 0, stream, idx, \
+                                (const T*)val, n, n_dev, rk, acc, touched, cell_lo, cells, clear_state, clear_n)); \
     } else {                                                                                                  \
-        SPB_CUDA_TRY(launch_pdl(axis_accumulate_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, idx, \
+        SPB_CUDA_TRY(launch_pdl(axis_accumulate_kernel<T, false>, dim3((unsigned)blocks), dim3(256), 0, stream, idx, \
                                 (const T*)val, n, n_dev, rk, acc, touched, cell_lo, cells, clear_state, clear_n)); \
     }                                                                                                         \
     break
@@ -347,6 +399,12 @@ static int launch_accumulate(int dtype, const int64_t* idx, const void* val, int
     return (int)cudaGetLastError();
 }
 
+static double __longlong_as_double_host(unsigned long long b) {
+    double d;
+    memcpy(&d, &b, sizeof(d));
+    return d;
+}
+
 // cells of [0, cells) relative to acc / touched (touched readable up to the next multiple of 64)
 static int64_t select_tiles(int64_t cells) { return ceil_div(cells, 256 * kSelCells); }
 
@@ -356,9 +414,10 @@ static int64_t select_groups(int64_t ntiles) { return ceil_div(ntiles, (int64_t)
 static size_t select_scratch_bytes(int64_t ntiles) { return (size_t)select_groups(ntiles) * 8 + (size_t)ntiles * 4; }
 
 // precleared: the producer launch zeroed the group counters (see the accumulate kernels)
+// touched == nullptr: sentinel mode.  clean: what an emitted cell is put back to.
 static int launch_select(double* acc, uint8_t* touched, int64_t cells, int64_t key_base, int64_t* out_idx,
                          double* out_sums, int64_t* out_count, spb_workspace* ws, cudaStream_t stream,
-                         bool precleared = false) {
+                         double clean, bool precleared = false) {
     const int64_t ntiles = select_tiles(cells);
     if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
     int rc = workspace_reserve(ws, select_scratch_bytes(ntiles), stream);
@@ -367,10 +426,10 @@ static int launch_select(double* acc, uint8_t* touched, int64_t cells, int64_t k
     sc.group_cnt = reinterpret_cast<unsigned long long*>(ws_state(ws));
     sc.counts = reinterpret_cast<int*>(sc.group_cnt + select_groups(ntiles));
     if (!precleared) SPB_CUDA_TRY(cudaMemsetAsync(sc.group_cnt, 0, (size_t)select_groups(ntiles) * 8, stream));
-    SPB_CUDA_TRY(launch_pdl(count_touched_kernel, dim3((unsigned)ntiles), dim3(256), 0, stream,
+    SPB_CUDA_TRY(launch_pdl(count_touched_kernel, dim3((unsigned)ntiles), dim3(256), 0, stream, (const double*)acc,
                             (const uint8_t*)touched, cells, sc));
     SPB_CUDA_TRY(launch_pdl(select_touched_kernel, dim3((unsigned)ntiles), dim3(256), 0, stream, acc, touched, cells,
-                            key_base, out_idx, out_sums, out_count, sc));
+                            key_base, out_idx, out_sums, out_count, sc, clean));
     SPB_LAUNCHED(2);
     return (int)cudaGetLastError();
 }
@@ -391,19 +450,30 @@ static int axis_sum_window(int dtype, const int64_t* idx, const void* val, int64
     if (rc) return rc;
     if (n == 0 || cells == 0) return (int)cudaMemsetAsync(out_count, 0, 8, stream);
     if (!idx || !val || !out_idx || !out_sums || !ws) return SPB_ERR_BAD_ARG;
-    // accumulators (cells doubles) then one flag byte per cell (padded to 64) in the workspace's self-cleaning slab
+    // Flags or sentinel?  Flags when the count is only an upper bound (a lazily counted producer: usually far
+    // fewer elements than that) or when few cells can be touched: scanning one byte per cell is what the
+    // emitting pass costs then.  Otherwise no flags: one scattered store less per element ...
+    // ... when the flag stores would scatter, that is: the finest axis group is kept and long enough that a
+    // warp's 32 consecutive elements land in 32 different sectors of the flag array (config 2, axis 0 or 1:
+    // runs of 2^22 / 2^14 cells).  With a short kept group behind the reduced axis (axis 2: 64 cells) the
+    // flag bytes of a warp share a sector or two and cost next to nothing, while the sentinel variant's
+    // emitting pass reads 8 bytes per cell instead of 1 (measured: 109 us with flags, 120 us without).
+    const bool scattered = ndim >= 2 && out_strides[ndim - 1] != 0 && in_strides[ndim - 2] >= 512;
+    const bool use_flags = n_dev != nullptr || n < cells / 4 || !scattered;
+    // accumulators (cells doubles, readable up to a multiple of 16 cells) and one flag byte per cell (padded to
+    // 64) in the workspace's self-cleaning buffers
     const size_t acc_bytes = ((size_t)cells * sizeof(double) + 255) & ~(size_t)255;
     const int64_t nflags = ceil_div(cells, 64) * 64;
-    rc = workspace_reserve_accum(ws, acc_bytes + (size_t)nflags, stream);
+    rc = workspace_reserve_accum(ws, acc_bytes, use_flags ? (size_t)nflags : 0, stream);
     if (rc) return rc;
-    // The slab is only all-zero again once the emitting pass has run: if an earlier call failed between
-    // its two launches, wipe it before anybody adds into it.
+    // The buffers are only clean again once the emitting pass has run: if an earlier call failed between
+    // its launches, wipe them before anybody adds into them.
     if (ws->accum_dirty) {
-        SPB_CUDA_TRY(cudaMemsetAsync(ws->accum, 0, ws->accum_bytes, stream));
-        ws->accum_dirty = 0;
+        rc = workspace_wipe_accum(ws, stream);
+        if (rc) return rc;
     }
     double* const acc = reinterpret_cast<double*>(ws->accum);
-    uint8_t* const touched = reinterpret_cast<uint8_t*>(ws->accum) + acc_bytes;
+    uint8_t* const touched = use_flags ? reinterpret_cast<uint8_t*>(ws->flags) : nullptr;
     ws->accum_dirty = 1;
     const int64_t ntiles = select_tiles(cells);
     if (ntiles > 0x7fffffffLL) return SPB_ERR_TOO_LARGE;
@@ -412,7 +482,8 @@ static int axis_sum_window(int dtype, const int64_t* idx, const void* val, int64
     rc = launch_accumulate(dtype, idx, val, n, n_dev, rk, cell_lo, cells, acc, touched, ws_state(ws),
                            select_groups(ntiles), stream);
     if (rc) return rc;
-    rc = launch_select(acc, touched, cells, cell_lo, out_idx, out_sums, out_count, ws, stream, true);
+    rc = launch_select(acc, touched, cells, cell_lo, out_idx, out_sums, out_count, ws, stream,
+                       __longlong_as_double_host(kNegZeroBits), true);
     if (rc == SPB_OK) ws->accum_dirty = 0;
     return rc;
 }
@@ -461,5 +532,5 @@ extern "C" int spb_emit_touched(double* acc, uint8_t* touched, int64_t cell_lo, 
     if (!acc || !touched || !out_idx || !out_sums || !ws) return SPB_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(touched) & 15) != 0) return SPB_ERR_BAD_ARG;
     return launch_select(acc + cell_lo, touched + cell_lo, cell_hi - cell_lo, cell_lo, out_idx, out_sums, out_count, ws,
-                         stream);
+                         stream, 0.0);
 }

@@ -31,8 +31,10 @@ struct spb_workspace {
     size_t payload_bytes;
     void* state16;        // 16-byte {tagged word, value} look-back entries (only ever written as such)
     size_t state16_bytes;
-    void* accum;          // dense accumulators + flags: all zero between calls (the consumer cleans what it reads)
-    size_t accum_bytes;
+    void* accum;          // dense float64 accumulators: every cell holds -0.0 ("untouched") between calls -- the
+    size_t accum_bytes;   // consumer puts back what it reads (see csrc/axis_sum.cu)
+    void* flags;          // one "touched" byte per cell for the sums that use flags: all zero between calls
+    size_t flags_bytes;
     int accum_dirty;      // an accumulate pass was enqueued whose emitting pass was not: wipe before the next use
     size_t last_state_bytes;     // look-back words / 16-byte entries the call in progress asked for: what a
     size_t last_state16_bytes;   // captured launch wipes before it runs (see workspace_next_epoch)
@@ -72,7 +74,9 @@ int workspace_reserve(spb_workspace* ws, size_t state_bytes, cudaStream_t stream
 int workspace_next_epoch(spb_workspace* ws, cudaStream_t stream, uint32_t* epoch, bool wipe_in_capture = true);
 int workspace_reserve_payload(spb_workspace* ws, size_t bytes, cudaStream_t stream);
 int workspace_reserve_state16(spb_workspace* ws, size_t bytes, cudaStream_t stream);
-int workspace_reserve_accum(spb_workspace* ws, size_t bytes, cudaStream_t stream);
+int workspace_reserve_accum(spb_workspace* ws, size_t acc_bytes, size_t flag_bytes, cudaStream_t stream);
+int workspace_wipe_accum(spb_workspace* ws, cudaStream_t stream);
+constexpr unsigned long long kNegZeroBits = 0x8000000000000000ull;     // bit pattern of -0.0
 int device_sm_count();
 inline uint64_t* ws_state(spb_workspace* ws) { return reinterpret_cast<uint64_t*>((char*)ws->dev + kWsMiscBytes); }
 inline char* ws_misc(spb_workspace* ws) { return (char*)ws->dev; }

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kRNT, 4) reduce_by_key_kernel(const ReducePara
         if (k < cnt) {
             const int64_t key = s_key[pad8(first + k)];
             seg[k] = (int64_t)fastdiv((uint64_t)key, p.div);
-            double val = (double)s_val[pad8(first + k)];
+            double val = (double)s_val[pad8(first + k)] + 0.0;     // (a stored -0.0 counts as +0.0, as in np.bincount)
             v[k] = val;
         }
     }

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kSlabNT, COUNT ? 6 : kSlabCtasPerSm) slab_last
                         }
                         ++slot;
                         s_key[slot] = (uint16_t)rel[k];
-                        run = (double)v[k];
+                        run = (double)v[k] + 0.0;          // (a stored -0.0 counts as +0.0, as in np.bincount)
                         mine = true;
                     } else {
                         run += (double)v[k];

@@ -75,20 +75,61 @@ int workspace_reserve_state16(spb_workspace* ws, size_t bytes, cudaStream_t stre
     return SPB_OK;
 }
 
-int workspace_reserve_accum(spb_workspace* ws, size_t bytes, cudaStream_t stream) {
+__global__ void __launch_bounds__(256) fill_u64_kernel(unsigned long long* p, size_t n, unsigned long long v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+static int fill_negzero(void* p, size_t bytes, cudaStream_t stream) {
+    const size_t n = bytes / 8;
+    size_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks > (size_t)device_sm_count() * 16) blocks = (size_t)device_sm_count() * 16;
+    if (blocks == 0) return SPB_OK;
+    fill_u64_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<unsigned long long*>(p), n, kNegZeroBits);
+    SPB_LAUNCHED(1);
+    return (int)cudaGetLastError();
+}
+
+// The dense accumulators of sum(axis): float64 cells that hold -0.0 between calls, and one flag byte per cell
+// (zero between calls) for the sums that mark touched cells with flags.  Users clean up after themselves.
+int workspace_reserve_accum(spb_workspace* ws, size_t acc_bytes, size_t flag_bytes, cudaStream_t stream) {
     if (!ws) return SPB_ERR_BAD_ARG;
-    if (ws->accum_bytes >= bytes && ws->accum) return SPB_OK;
-    SPB_NO_GROWTH_IN_CAPTURE(stream);
-    if (ws->accum) {
-        SPB_CUDA_TRY(cudaStreamSynchronize(stream));
-        SPB_CUDA_TRY(cudaFree(ws->accum));
-        ws->accum = nullptr;
-        ws->accum_bytes = 0;
+    if (ws->accum_bytes < acc_bytes || !ws->accum) {
+        SPB_NO_GROWTH_IN_CAPTURE(stream);
+        if (ws->accum) {
+            SPB_CUDA_TRY(cudaStreamSynchronize(stream));
+            SPB_CUDA_TRY(cudaFree(ws->accum));
+            ws->accum = nullptr;
+            ws->accum_bytes = 0;
+        }
+        const size_t want = (acc_bytes + acc_bytes / 4 + (1u << 20) + 255) & ~(size_t)255;
+        SPB_CUDA_TRY(cudaMalloc(&ws->accum, want));
+        const int rc = fill_negzero(ws->accum, want, stream);
+        if (rc) return rc;
+        ws->accum_bytes = want;
     }
-    const size_t want = (bytes + bytes / 4 + (1u << 20) + 255) & ~(size_t)255;
-    SPB_CUDA_TRY(cudaMalloc(&ws->accum, want));
-    SPB_CUDA_TRY(cudaMemsetAsync(ws->accum, 0, want, stream));     // zero from here on: users clean up after themselves
-    ws->accum_bytes = want;
+    if (flag_bytes && (ws->flags_bytes < flag_bytes || !ws->flags)) {
+        SPB_NO_GROWTH_IN_CAPTURE(stream);
+        if (ws->flags) {
+            SPB_CUDA_TRY(cudaStreamSynchronize(stream));
+            SPB_CUDA_TRY(cudaFree(ws->flags));
+            ws->flags = nullptr;
+            ws->flags_bytes = 0;
+        }
+        const size_t want = (flag_bytes + flag_bytes / 4 + (1u << 16) + 255) & ~(size_t)255;
+        SPB_CUDA_TRY(cudaMalloc(&ws->flags, want));
+        SPB_CUDA_TRY(cudaMemsetAsync(ws->flags, 0, want, stream));
+        ws->flags_bytes = want;
+    }
+    return SPB_OK;
+}
+
+// back to the clean state after a call that failed between its accumulating and its emitting launch
+int workspace_wipe_accum(spb_workspace* ws, cudaStream_t stream) {
+    if (ws->accum) {
+        const int rc = fill_negzero(ws->accum, ws->accum_bytes, stream);
+        if (rc) return rc;
+    }
+    if (ws->flags) SPB_CUDA_TRY(cudaMemsetAsync(ws->flags, 0, ws->flags_bytes, stream));
     ws->accum_dirty = 0;
     return SPB_OK;
 }
@@ -148,6 +189,8 @@ int spb_workspace_create(spb_workspace** ws) {
     w->state16_bytes = 0;
     w->accum = nullptr;
     w->accum_bytes = 0;
+    w->flags = nullptr;
+    w->flags_bytes = 0;
     w->accum_dirty = 0;
     w->last_state_bytes = 0;
     w->last_state16_bytes = 0;
@@ -161,6 +204,7 @@ int spb_workspace_destroy(spb_workspace* ws) {
     if (ws->payload) cudaFree(ws->payload);
     if (ws->state16) cudaFree(ws->state16);
     if (ws->accum) cudaFree(ws->accum);
+    if (ws->flags) cudaFree(ws->flags);
     delete ws;
     return SPB_OK;
 }

@@ -194,6 +194,44 @@ def test_sum_axis_slab_ignores_indices_past_the_shape(sp):
     np.testing.assert_array_equal(ov[:m].cpu().numpy(), want[want > 0])
 
 
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_sum_axis_zero_sums_survive(sp, axis):
+    """Dense path without flags (accumulators start at -0.0 as the "untouched" mark): stored zeros of either sign,
+    sums that cancel exactly, NaN and inf must all come out as stored elements, with +0.0 where numpy's
+    bincount gives +0.0 -- and an untouched cell must not."""
+    from sparray_b200 import _kernels as k
+    rng = np.random.default_rng(5 + axis)
+    shape = (12, 16, 1024)               # a long innermost axis: the flag-less variant applies to axes 0 and 1
+    cells = 12 * 16 * 1024 // shape[axis]
+    idx = np.unique(rng.integers(0, 12 * 16 * 1024, size=2 * cells, dtype=np.int64))   # ~2 elements per output cell
+    val = rng.standard_normal(len(idx))
+    val[::5] = 0.0
+    val[1::5] = -0.0
+    val[2::50] = np.nan
+    val[3::70] = np.inf
+    # pairs that cancel exactly: two elements of the same output cell with opposite values
+    coords = np.array(np.unravel_index(idx, shape))
+    keep = [a for a in range(3) if a != axis]
+    out_key = np.ravel_multi_index(coords[keep], [shape[a] for a in keep])
+    order = np.argsort(out_key, kind="stable")
+    same = np.nonzero(out_key[order][1:] == out_key[order][:-1])[0][::3]
+    val[order[same + 1]] = -val[order[same]]
+    A = sp.FlatSparray(idx, val, shape=shape, is_canonical=True)
+    assert len(idx) >= cells // 4 and k.dense_sum_cells(shape, axis)
+    got = A.sum(axis=axis)
+    wi, wd, ws = fo.sum_axis(idx, val, shape, axis)
+    gi, gd = to_np(got.indices), to_np(got.data)
+    np.testing.assert_array_equal(gi, wi)
+    np.testing.assert_array_equal(np.isnan(gd), np.isnan(wd))
+    ok = ~np.isnan(wd)
+    np.testing.assert_allclose(gd[ok], wd[ok], rtol=1e-12, atol=1e-12)
+    zero = ok & (wd == 0) & (gd == 0)            # (a different order of additions may leave a rounding residue)
+    assert zero.sum() > min(100, cells // 8)
+    np.testing.assert_array_equal(np.signbit(gd[zero]), np.signbit(wd[zero]))
+    # twice: the accumulators were handed back clean
+    np.testing.assert_array_equal(to_np(A.sum(axis=axis).indices), wi)
+
+
 def test_config2_chain(sp):
     """BASELINE config 2 at full size: c = a*b (intersection) then c.sum(axis=2); also a.sum(axis=2)."""
     shape = (256, 256, 256, 64)
