@@ -64,6 +64,12 @@ struct HistParams {
     int bins[kMaxPasses];
     uint64_t* hist;             // [kMaxPasses][256] counts (zeroed by the caller)
     int p32;                    // packed keys are re-keyed in 32-bit registers (power-of-two shape, < 2^32 cells)
+    // Pre-keying: this kernel re-keys every key anyway, so it also leaves what the FIRST pass would otherwise have
+    // to compute again from the 8-byte keys -- the 32-bit packed key (squeeze mode: with the first digit taken
+    // out, and that digit in a byte beside it).  The first pass then costs what a middle pass costs.
+    uint32_t* pre_keys;         // [n], or null
+    uint8_t* pre_dig;           // [n] squeeze mode, else null
+    int pre_width;              // squeeze mode: width of the first digit
 };
 
 // ---- all digit histograms in one read --------------------------------------------------------
@@ -100,6 +106,23 @@ __global__ void __launch_bounds__(kSNT) radix_hist_kernel(const HistParams p) {
         for (int u = 0; u < kHistUnroll; ++u) {
             if constexpr (P32) P[u] = apply_rekey32(raw[u], p.rk);
             else P[u] = pack_key(apply_rekey(raw[u], p.rk), p.pk);
+        }
+        if (p.pre_keys) {                              // (uniform)
+#pragma unroll
+            for (int u = 0; u < kHistUnroll; ++u) {
+                const int64_t i = i0 + u * nthreads;
+                if (valid[u]) {
+                    if (p.pre_dig) {
+                        const uint64_t P64 = (uint64_t)P[u];
+                        const int sh = p.shift[0];
+                        const uint64_t lo = P64 & ((1ull << sh) - 1ull);
+                        p.pre_keys[i] = (uint32_t)(((P64 >> (sh + p.pre_width)) << sh) | lo);
+                        p.pre_dig[i] = (uint8_t)((P64 >> sh) & ((1u << p.pre_width) - 1u));
+                    } else {
+                        p.pre_keys[i] = (uint32_t)P[u];
+                    }
+                }
+            }
         }
 #pragma unroll
         for (int u = 0; u < kHistUnroll; ++u) {
@@ -184,6 +207,8 @@ struct PassParams {
     uint32_t epoch;
     int vals_aligned;           // vals_in is 16-byte aligned: full tiles are fetched by TMA
     int p32;                    // FIRST: re-key in 32-bit registers (see run_sort)
+    const uint32_t* pre_keys;   // FIRST: the histogram kernel left the packed keys here (and, squeeze mode, the
+    const uint8_t* pre_dig;     // digits of this pass): nothing is re-keyed
 };
 
 template <int VB> struct ValType;
@@ -323,6 +348,14 @@ __global__ void __launch_bounds__(kSNT, PassCfg<K32, VB>::kMinCtas) radix_pass_k
         dr[k] = dmask;
         if (e < items) {
             if constexpr (FIRST) {
+                if constexpr (K32 && !LAST) {
+                    if (p.pre_keys) {              // (uniform) pre-keyed by the histogram kernel
+                        const uint32_t pkd = __ldcs(p.pre_keys + base + e);
+                        key[k] = (KS)pkd;
+                        dr[k] = p.pre_dig ? (unsigned)__ldcs(p.pre_dig + base + e) : ((pkd >> p.in_shift) & dmask);
+                        continue;
+                    }
+                }
                 const int64_t raw = __ldcs(reinterpret_cast<const int64_t*>(p.keys_in) + base + e);
                 if constexpr (K32) {
                     if (p.p32) {                   // (uniform) P == new key < 2^32, nothing squeezed
@@ -651,6 +684,20 @@ int run_sort(const int64_t* idx, const void* val, int64_t n, const Rekey& rk, ui
     // power-of-two shape whose new keys fit 32 bits: the re-key runs in 32-bit registers
     const bool p32 = rk.ndim > 0 && rk.pow2 && rk.out32 && pk.pow2 && pl.total_bits <= 32;
     hp.p32 = p32;
+    // Pre-keying (two passes or more, 32-bit intermediate keys): the histogram kernel leaves the packed keys -- and
+    // in squeeze mode the first digits -- in the scratch array the first pass does NOT write to (the second pass
+    // will overwrite it: by then it has been consumed).  4n (+ n) of its 8n bytes.
+    const bool to_final0 = ((np - 1) % 2) == 0;
+    uint32_t* pre_keys = nullptr;
+    uint8_t* pre_dig = nullptr;
+    if (np >= 2 && pl.mode != MODE_WIDE) {
+        char* const buf = reinterpret_cast<char*>(to_final0 ? tmp_idx : out_idx);
+        pre_keys = reinterpret_cast<uint32_t*>(buf);
+        if (pl.mode == MODE_SQUEEZE) pre_dig = reinterpret_cast<uint8_t*>(buf + (size_t)n * 4);
+    }
+    hp.pre_keys = pre_keys;
+    hp.pre_dig = pre_dig;
+    hp.pre_width = pl.sq_width;
     {
         const dim3 hg((unsigned)hblocks), hb(kSNT);
         cudaError_t e;
@@ -692,6 +739,8 @@ int run_sort(const int64_t* idx, const void* val, int64_t n, const Rekey& rk, ui
         // previous digit, which sat right below it
         p.in_shift = pl.lowbits + pl.shift[ps] - ((p.squeeze && !first) ? pl.sq_width : 0);
         p.vals_aligned = VB ? ((reinterpret_cast<uintptr_t>(vin) & 15) == 0) : 0;
+        p.pre_keys = first ? pre_keys : nullptr;
+        p.pre_dig = first ? pre_dig : nullptr;
         rc = workspace_next_epoch(ws, stream, &p.epoch);
         if (rc) return rc;
         rc = k32 ? launch_pass_fl<true, VB>(first, last, p, ntiles, stream)
