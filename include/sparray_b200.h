@@ -32,7 +32,11 @@ typedef struct CUstream_st* spb_stream_t;   /* == cudaStream_t */
 /* value dtypes (numpy names) */
 enum spb_dtype {
     SPB_F32 = 0, SPB_F64 = 1, SPB_I32 = 2, SPB_I64 = 3, SPB_U8 = 4, SPB_BOOL = 5, SPB_I8 = 6, SPB_I16 = 7,
-    SPB_DTYPE_COUNT = 8
+    /* conversion-only dtypes: spb_cast accepts them on either side; every other entry point works on the
+     * dtypes above.  The host widens them for arithmetic (float16 -> float32, uint16 -> int32, uint32 -> int64)
+     * and passes them as same-sized integers to the kernels that only move values. */
+    SPB_F16 = 8, SPB_U16 = 9, SPB_U32 = 10, SPB_U64 = 11,
+    SPB_DTYPE_COUNT = 12
 };
 
 /* binary value ops fused into the set merges (numpy ufunc semantics incl. NaN / signed zero) */

@@ -97,6 +97,21 @@ def len_range(start, stop, step):
 # ---- section 2: fused sparse (op) sparse ----------------------------------------------------
 
 _WIDEN = {torch.bool: torch.int32, torch.uint8: torch.int32, torch.int8: torch.int32, torch.int16: torch.int32}
+_WIDEN.update(dt.COMPUTE)          # float16, uint16 / 32 / 64: no kernels of their own (see _dtypes.py)
+
+
+def _bits(t):
+    """same-sized integer view of a conversion-only dtype, for kernels that only move values"""
+    return t.view(dt.BITS[t.dtype]) if t is not None and t.dtype in dt.BITS else t
+
+
+def _wide(t):
+    """arithmetic carrier of a conversion-only dtype"""
+    return cast(t, dt.COMPUTE[t.dtype]) if t.dtype in dt.COMPUTE else t
+
+
+def _back(t, orig):
+    return cast(t, orig) if orig in dt.COMPUTE and t.dtype != orig else t
 
 
 def setop_binop(kind, op, a_idx, a_val, b_idx, b_val, lazy=False):
@@ -133,6 +148,12 @@ def setop_binop(kind, op, a_idx, a_val, b_idx, b_val, lazy=False):
 
 def unary_map(op, data, scalar=0):
     require_cuda()
+    if data.dtype in dt.COMPUTE:
+        orig = data.dtype
+        if orig == torch.float16 and op.endswith("_s"):
+            scalar = float(np.float16(scalar))     # numpy rounds a Python scalar to the array's float16 first
+        out = unary_map(op, _wide(data), scalar)
+        return out if out.dtype == torch.bool else _back(out, orig)
     out_dtype = torch.bool if op.endswith("_s") and op[:2] in ("lt", "le", "gt", "ge", "eq", "ne") else data.dtype
     out = torch.empty_like(data, dtype=out_dtype)
     is_float = data.dtype.is_floating_point
@@ -146,13 +167,15 @@ def cast(data, dtype):
     if data.dtype == dtype:
         return data.clone()          # device-to-device memcpy
     out = torch.empty_like(data, dtype=dtype)
-    check(lib.spb_cast(dt.spb_dtype(data.dtype), dt.spb_dtype(dtype), ptr(data), ptr(out), data.numel(), stream()))
+    check(lib.spb_cast(dt.spb_cast_dtype(data.dtype), dt.spb_cast_dtype(dtype), ptr(data), ptr(out), data.numel(),
+                       stream()))
     return out
 
 
 def scatter_dense(idx, val, size):
     require_cuda()
     dense = torch.zeros(int(size), dtype=val.dtype, device=val.device)   # cudaMemset: plumbing
+    val = _bits(val)
     check(lib.spb_scatter_dense(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), idx.numel(), ptr(dense), stream()))
     return dense
 
@@ -160,6 +183,7 @@ def scatter_dense(idx, val, size):
 def scatter_into(dense, idx, val):
     """dense[idx[i]] = val[i] in place (dense is a flat device tensor of val's dtype)."""
     require_cuda()
+    val = _bits(val)
     check(lib.spb_scatter_dense(dt.spb_dtype(val.dtype), ptr(idx), ptr(val), idx.numel(), ptr(dense), stream()))
     return dense
 
@@ -167,7 +191,7 @@ def scatter_into(dense, idx, val):
 def gather(src, pos):
     require_cuda()
     out = torch.empty(pos.numel(), dtype=src.dtype, device=src.device)
-    check(lib.spb_gather(dt.spb_dtype(src.dtype), ptr(src), ptr(pos), pos.numel(), ptr(out), stream()))
+    check(lib.spb_gather(dt.spb_dtype(_bits(src).dtype), ptr(src), ptr(pos), pos.numel(), ptr(out), stream()))
     return out
 
 
@@ -182,6 +206,9 @@ def lower_bound(sorted_idx, query, want_found=True):
 
 def select_nonzero(dense_flat):
     require_cuda()
+    if dense_flat.dtype in dt.COMPUTE:
+        idx, val = select_nonzero(_wide(dense_flat))
+        return idx, _back(val, dense_flat.dtype)
     n = dense_flat.numel()
     idx = torch.empty(n, dtype=torch.int64, device=dense_flat.device)
     val = torch.empty(n, dtype=dense_flat.dtype, device=dense_flat.device)
@@ -195,6 +222,7 @@ def select_nonzero(dense_flat):
 def sum_all(data):
     """Returns a python float (float dtypes, float64 accumulate) or int."""
     require_cuda()
+    data = _wide(data)
     is_float = data.dtype.is_floating_point
     out = torch.empty(1, dtype=torch.float64 if is_float else torch.int64, device=data.device)
     check(lib.spb_sum_all(dt.spb_dtype(data.dtype), ptr(data), data.numel(), ptr(out), workspace(), stream()))
@@ -203,6 +231,9 @@ def sum_all(data):
 
 def select_pairs(idx, val, keep):
     require_cuda()
+    if val.dtype in dt.BITS:
+        oi, ov = select_pairs(idx, _bits(val), keep)
+        return oi, ov.view(val.dtype)
     n = idx.numel()
     out_idx = torch.empty(n, dtype=torch.int64, device=idx.device)
     out_val = torch.empty(n, dtype=val.dtype, device=idx.device)
@@ -217,6 +248,8 @@ def min_max(data, which):
     require_cuda()
     if data.numel() == 0:
         raise ValueError("zero-size array to reduction operation %s which has no identity" % which)
+    if data.dtype in dt.COMPUTE:
+        return dt.np_dtype(data.dtype).type(min_max(_wide(data), which))
     out = torch.empty(1, dtype=data.dtype, device=data.device)
     check(lib.spb_min_max(dt.spb_dtype(data.dtype), ptr(data), data.numel(), int(which == "max"), ptr(out),
                           workspace(), stream()))
@@ -228,6 +261,7 @@ def min_max(data, which):
 def reduce_by_key(keys, vals, divisor=1):
     """Sorted keys -> (unique keys // divisor, float64 sums)."""
     require_cuda()
+    vals = _wide(vals)
     n = keys.numel()
     out_keys = torch.empty(n, dtype=torch.int64, device=keys.device)
     out_sums = torch.empty(n, dtype=torch.float64, device=keys.device)
@@ -254,6 +288,12 @@ def spmv(idx, val, ncols, nrows, x, vdtype):
 
 
 def spgemm(a_idx, a_val, m, k, b_idx, b_val, n):
+    if a_val.dtype in dt.COMPUTE:
+        a_val, b_val = _wide(a_val), _wide(b_val)     # (the caller casts the result to the promoted dtype)
+    return _spgemm(a_idx, a_val, m, k, b_idx, b_val, n)
+
+
+def _spgemm(a_idx, a_val, m, k, b_idx, b_val, n):
     """C = A (m x k) . B (k x n) on sorted flat indices -> canonical (indices, values) of C (m x n):
     expand / sort / compress, the O(products) form of flat.py:545-561.  Values share one dtype."""
     require_cuda()
@@ -286,6 +326,9 @@ def spgemm(a_idx, a_val, m, k, b_idx, b_val, n):
 def rekey_sort(idx, val, in_strides, out_strides, sort_divisor, sort_bits):
     """(new keys sorted, values permuted alike); inputs untouched."""
     require_cuda()
+    if val is not None and val.dtype in dt.BITS:
+        oi, ov = rekey_sort(idx, _bits(val), in_strides, out_strides, sort_divisor, sort_bits)
+        return oi, ov.view(val.dtype)
     from . import _plan
     n = idx.numel()
     out_idx = torch.empty_like(idx)
@@ -403,6 +446,7 @@ def slab_geometry(shape, axis):
 
 def axis_sum_slab(idx, val, slab, cap):
     require_cuda()
+    val = _wide(val)
     out_idx = torch.empty(cap, dtype=torch.int64, device=idx.device)
     out_sums = torch.empty(cap, dtype=torch.float64, device=idx.device)
     cnt = torch.empty(1, dtype=torch.int64, device=idx.device)
@@ -423,6 +467,7 @@ def _stride_args(in_strides, out_strides):
 
 def axis_sum_dense(idx, val, in_strides, out_strides, cell_lo, cell_hi, n_dev=None):
     require_cuda()
+    val = _wide(val)
     n = idx.numel()
     cap = min(n, cell_hi - cell_lo)
     out_idx = torch.empty(cap, dtype=torch.int64, device=idx.device)
@@ -436,6 +481,7 @@ def axis_sum_dense(idx, val, in_strides, out_strides, cell_lo, cell_hi, n_dev=No
 
 
 def axis_accumulate(idx, val, in_strides, out_strides, cells):
+    val = _wide(val)
     """Local half of a sharded dense axis sum: (float64 accumulators [cells], flag bytes [cells padded
     to 64]) holding this shard's contributions; to be all-reduced (SUM / MAX) across ranks."""
     require_cuda()
@@ -483,6 +529,9 @@ def canonicalize(idx, val, max_key=None):
 def getitem_box(idx, val, shape, ranges, new_shape):
     """ints + slices: one pass over the stored elements inside the box's flat-index span."""
     require_cuda()
+    if val.dtype in dt.BITS:
+        oi, ov = getitem_box(idx, _bits(val), shape, ranges, new_shape)
+        return oi, ov.view(val.dtype)
     ranges = np.ascontiguousarray(ranges, dtype=np.int64)
     shape_arr = np.ascontiguousarray(shape, dtype=np.int64)
     strides = np.ones(len(shape), dtype=object)
@@ -520,6 +569,9 @@ def outer_sum(offsets, new_shape, device):
 
 def lookup_compact(sorted_idx, val, query):
     require_cuda()
+    if val.dtype in dt.BITS:
+        oi, ov = lookup_compact(sorted_idx, _bits(val), query)
+        return oi, ov.view(val.dtype)
     nq = query.numel()
     out_idx = torch.empty(nq, dtype=torch.int64, device=query.device)
     out_val = torch.empty(nq, dtype=val.dtype, device=query.device)
@@ -536,6 +588,9 @@ def binary_map(op, a, b):
     """Elementwise a (op) b on two aligned device vectors of one dtype."""
     require_cuda()
     assert a.dtype == b.dtype and a.numel() == b.numel()
+    if a.dtype in dt.COMPUTE:
+        out = binary_map(op, _wide(a), _wide(b))
+        return out if out.dtype == torch.bool else _back(out, a.dtype)
     out = torch.empty_like(a, dtype=torch.bool if op in dt.COMPARISONS else a.dtype)
     check(lib.spb_binary_map(dt.BINOPS[op], dt.spb_dtype(a.dtype), ptr(a), ptr(b), ptr(out), a.numel(), stream()))
     return out
@@ -544,6 +599,9 @@ def binary_map(op, a, b):
 def broadcast_expand(idx, val, in_shape, out_shape):
     """Unsorted (index, value) pairs of the array broadcast from in_shape (left-padded) to out_shape."""
     require_cuda()
+    if val.dtype in dt.BITS:
+        oi, ov = broadcast_expand(idx, _bits(val), in_shape, out_shape)
+        return oi, ov.view(val.dtype)
     ins = np.ascontiguousarray(in_shape, dtype=np.int64)
     outs = np.ascontiguousarray(out_shape, dtype=np.int64)
     reps = int(np.prod([o for i, o in zip(ins, outs) if i == 1 and o > 1], dtype=object))

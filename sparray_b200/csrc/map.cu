@@ -4,6 +4,10 @@
 // (flat.py:262-267).  128-bit vectorised where the pointers allow it.
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
 #include <math.h>
 
 namespace spb {
@@ -219,12 +223,32 @@ __global__ void __launch_bounds__(kMapThreads) binary_kernel(const T* __restrict
     }
 }
 
+// value conversion like numpy's astype: one rounding (double -> half goes through __double2half, not through float)
+template <typename TI, typename TO>
+__device__ __forceinline__ TO convert_value(TI x) {
+    if constexpr (std::is_same<TI, __half>::value && std::is_same<TO, __half>::value) {
+        return x;
+    } else if constexpr (std::is_same<TI, __half>::value) {
+        return (TO)__half2float(x);
+    } else if constexpr (std::is_same<TO, __half>::value) {
+        if constexpr (std::is_same<TI, double>::value) return __double2half(x);
+        else return __float2half_rn((float)x);        // integers beyond 2^24 are far past the largest half anyway
+    } else {
+        return (TO)x;
+    }
+}
+template <typename TI>
+__device__ __forceinline__ bool is_nonzero(TI x) {
+    if constexpr (std::is_same<TI, __half>::value) return __half2float(x) != 0.0f;
+    else return x != TI(0);
+}
+
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(kMapThreads) cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n,
                                                            int to_bool) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        TI x = in[i];
-        out[i] = to_bool ? (TO)(x != TI(0)) : (TO)x;
+        const TI x = in[i];
+        out[i] = to_bool ? (TO)(is_nonzero<TI>(x) ? 1 : 0) : convert_value<TI, TO>(x);
     }
 }
 
@@ -454,8 +478,19 @@ int spb_cast(int dtype_in, int dtype_out, const void* in, void* out, int64_t n, 
             case SPB_BOOL: SPB_CAST_OUT(uint8_t);         \
             case SPB_I8: SPB_CAST_OUT(int8_t);            \
             case SPB_I16: SPB_CAST_OUT(int16_t);          \
+            case SPB_F16: SPB_CAST_OUT(__half);           \
+            case SPB_U16: SPB_CAST_OUT(uint16_t);         \
+            case SPB_U32: SPB_CAST_OUT(uint32_t);         \
+            case SPB_U64: SPB_CAST_OUT(uint64_t);         \
             default: return SPB_ERR_UNSUPPORTED;          \
         }                                                 \
+    }
+    switch (dtype_in) {                                   /* the conversion-only dtypes first */
+        case SPB_F16: SPB_CAST_IN(__half);
+        case SPB_U16: SPB_CAST_IN(uint16_t);
+        case SPB_U32: SPB_CAST_IN(uint32_t);
+        case SPB_U64: SPB_CAST_IN(uint64_t);
+        default: break;
     }
     SPB_DISPATCH_DTYPE(dtype_in, SPB_CAST_IN)
 #undef SPB_CAST_IN

@@ -745,6 +745,8 @@ class FlatSparray(_BaseSparray):
             total = _k.sum_all(self.data)
             if dtype == np.bool_:
                 return np.bool_(total != 0)
+            if dtype.kind in "iu":
+                return np.int64(total).astype(dtype)       # data.sum(dtype=self.dtype) wraps like the dtype (flat.py:608-610)
             return dtype.type(total)
         # float64 output whatever the input dtype, like np.bincount(weights=)
         if self._pending is not None and _k.dense_sum_cells(self.shape, axis):

@@ -232,6 +232,57 @@ def test_sum_axis_zero_sums_survive(sp, axis):
     np.testing.assert_array_equal(to_np(A.sum(axis=axis).indices), wi)
 
 
+@pytest.mark.parametrize("dtype", [np.float16, np.uint16, np.uint32, np.uint64], ids=lambda d: np.dtype(d).name)
+def test_conversion_only_dtypes(sp, dtype):
+    """float16 and the unsigned integers have no kernels of their own: arithmetic runs on a wider carrier
+    (float32 / int32 / int64) and is narrowed back, value-moving kernels see same-sized integers.  Against numpy on
+    the dense arrays, bit for bit (one float16 op through float32 rounds like numpy's own float16 loops)."""
+    rng = np.random.default_rng(int(np.dtype(dtype).itemsize) * 7 + ord(np.dtype(dtype).kind))
+    shape = (23, 17, 9)
+    dt_ = np.dtype(dtype)
+
+    def dense():
+        d = np.zeros(shape, dtype=dt_)
+        m = rng.random(shape) < 0.3
+        if dt_.kind == "f":
+            d[m] = rng.standard_normal(int(m.sum())).astype(dt_)
+        else:
+            d[m] = rng.integers(1, 200, size=int(m.sum())).astype(dt_)
+        return d
+    da, db = dense(), dense()
+    A, B = sp.FlatSparray.from_ndarray(da), sp.FlatSparray.from_ndarray(db)
+    assert A.dtype == dt_ and np.array_equal(A.toarray(), da)
+    for name, got, want in [
+            ("add", A + B, da + db), ("sub", A - B, da - db), ("mul", A * B, da * db),
+            ("min", A.minimum(B), np.minimum(da, db)), ("max", A.maximum(B), np.maximum(da, db)),
+            ("transpose", A.transpose(2, 0, 1), da.transpose(2, 0, 1)), ("T", A.T, da.T),
+            ("row", A[3], da[3]), ("box", A[2:20:3, :, 1:7], da[2:20:3, :, 1:7]),
+            ("scalar", A * 3, da * dt_.type(3)), ("astype", A.astype(np.float64), da.astype(np.float64)),
+            ("ne", A != B, da != db), ("lt", A < B, da < db)]:
+        g = got.toarray() if hasattr(got, "toarray") else np.asarray(got)
+        assert g.dtype == want.dtype, (name, g.dtype, want.dtype)
+        np.testing.assert_array_equal(g, want, err_msg=name)
+    for axis in range(3):
+        np.testing.assert_allclose(A.sum(axis=axis).toarray(), da.astype(np.float64).sum(axis=axis), rtol=1e-12, err_msg="sum")
+    total = A.sum()                                # data.sum(dtype=self.dtype), flat.py:608-610: wraps for small integers
+    assert total.dtype == dt_
+    np.testing.assert_allclose(float(total), float(da.sum(dtype=dt_)), rtol=2e-3 if dt_.kind == "f" else 0)
+    assert A.max() == da[da != 0].max() and A.min() == da[da != 0].min()        # over the stored elements (flat.py:719-725)
+    x = rng.standard_normal(9).astype(np.float64)
+    np.testing.assert_allclose(to_np(A.reshape((23 * 17, 9)).dot(x)), da.reshape(23 * 17, 9).astype(np.float64).dot(x), rtol=1e-10, atol=1e-10)
+    C = A.copy()
+    C[1, 2] = dt_.type(5)
+    want = da.copy()
+    want[1, 2] = 5
+    np.testing.assert_array_equal(C.toarray(), want)
+    # non-canonical ctor: duplicates are summed
+    idx = np.array([5, 3, 5, 9, 3], dtype=np.int64)
+    val = np.array([1, 2, 3, 4, 5]).astype(dt_)
+    D = sp.FlatSparray(idx, val, shape=(12,))
+    np.testing.assert_array_equal(to_np(D.indices), [3, 5, 9])
+    np.testing.assert_array_equal(to_np(D.data), np.array([7, 4, 4]).astype(dt_))
+
+
 def test_config2_chain(sp):
     """BASELINE config 2 at full size: c = a*b (intersection) then c.sum(axis=2); also a.sum(axis=2)."""
     shape = (256, 256, 256, 64)
