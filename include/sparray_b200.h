@@ -155,6 +155,12 @@ int spb_binary_map(int op, int dtype, const void* a, const void* b, void* out, i
 /* astype (flat.py:713-714) */
 int spb_cast(int dtype_in, int dtype_out, const void* in, void* out, int64_t n, spb_stream_t stream);
 
+/* complex64 / complex128 values (numpy's interleaved re, im storage) <-> two real arrays of real_dtype (SPB_F32 /
+ * SPB_F64).  The only complex-aware entry points: the host composes every complex operation of FlatSparray from the
+ * real kernels on the two parts, which always share one index array (flat.py:19-42 accepts any numpy dtype). */
+int spb_complex_split(int real_dtype, const void* c, int64_t n, void* re, void* im, spb_stream_t stream);
+int spb_complex_join(int real_dtype, const void* re, const void* im, int64_t n, void* c, spb_stream_t stream);
+
 /* toarray (flat.py:74-77): dense[idx[i]] = val[i]; dense is pre-zeroed by the caller */
 int spb_scatter_dense(int dtype, const int64_t* idx, const void* val, int64_t n, void* dense,
                       spb_stream_t stream);

@@ -22,7 +22,10 @@ _TORCH_TO_NP = {
     torch.float32: np.float32, torch.float64: np.float64, torch.int32: np.int32, torch.int64: np.int64,
     torch.uint8: np.uint8, torch.bool: np.bool_, torch.int8: np.int8, torch.int16: np.int16,
     torch.float16: np.float16, torch.uint16: np.uint16, torch.uint32: np.uint32, torch.uint64: np.uint64,
+    # containers only (sparray_b200/_complex.py): no kernel takes them, spb_dtype() refuses them
+    torch.complex64: np.complex64, torch.complex128: np.complex128,
 }
+COMPLEX_PART = {torch.complex64: torch.float32, torch.complex128: torch.float64}
 _NP_TO_TORCH = {np.dtype(v): k for k, v in _TORCH_TO_NP.items()}
 
 # enum spb_binop

@@ -172,6 +172,25 @@ def cast(data, dtype):
     return out
 
 
+def complex_split(c):
+    """complex device tensor (any shape, contiguous) -> (re, im) real tensors of the same shape"""
+    require_cuda()
+    part = dt.COMPLEX_PART[c.dtype]
+    re = torch.empty(c.shape, dtype=part, device=c.device)
+    im = torch.empty(c.shape, dtype=part, device=c.device)
+    check(lib.spb_complex_split(dt.spb_dtype(part), ptr(c), c.numel(), ptr(re), ptr(im), stream()))
+    return re, im
+
+
+def complex_join(re, im):
+    require_cuda()
+    assert re.dtype == im.dtype and re.shape == im.shape
+    ctype = {torch.float32: torch.complex64, torch.float64: torch.complex128}[re.dtype]
+    c = torch.empty(re.shape, dtype=ctype, device=re.device)
+    check(lib.spb_complex_join(dt.spb_dtype(re.dtype), ptr(re), ptr(im), re.numel(), ptr(c), stream()))
+    return c
+
+
 def scatter_dense(idx, val, size):
     require_cuda()
     dense = torch.zeros(int(size), dtype=val.dtype, device=val.device)   # cudaMemset: plumbing

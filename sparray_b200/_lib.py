@@ -77,6 +77,8 @@ PROTOTYPES = {
     "spb_axis_accumulate": (c_int, [c_int, c_p, c_p, c_i64, c_int, c_p, c_p, c_i64, c_p, c_p, c_p]),
     "spb_emit_touched": (c_int, [c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p]),
     "spb_axis_sum_slab_ok": (c_int, [c_i64, c_i64, c_i64, c_i64]),
+    "spb_complex_split": (c_int, [c_int, c_p, c_i64, c_p, c_p, c_p]),
+    "spb_complex_join": (c_int, [c_int, c_p, c_p, c_i64, c_p, c_p]),
     "spb_axis_sum_slab": (c_int, [c_int, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p]),
     "spb_getitem_box": (c_int, [c_int, c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "spb_outer_sum": (c_int, [c_p, c_int, c_p, c_p, c_i64, c_p]),

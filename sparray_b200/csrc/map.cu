@@ -252,6 +252,25 @@ __global__ void __launch_bounds__(kMapThreads) cast_kernel(const TI* __restrict_
     }
 }
 
+// complex storage (re, im interleaved) <-> two real arrays: the only complex-aware kernels -- every complex
+// operation is composed from the real kernels on the two parts (sparray_b200/_complex.py)
+template <typename T>
+__global__ void __launch_bounds__(kMapThreads) complex_split_kernel(const T* __restrict__ c, int64_t n, T* __restrict__ re,
+                                                                    T* __restrict__ im) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        re[i] = c[2 * i];
+        im[i] = c[2 * i + 1];
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(kMapThreads) complex_join_kernel(const T* __restrict__ re, const T* __restrict__ im,
+                                                                   int64_t n, T* __restrict__ c) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        c[2 * i] = re[i];
+        c[2 * i + 1] = im[i];
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kMapThreads) scatter_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
                                                               int64_t n, T* __restrict__ dense) {
@@ -495,6 +514,30 @@ int spb_cast(int dtype_in, int dtype_out, const void* in, void* out, int64_t n, 
     SPB_DISPATCH_DTYPE(dtype_in, SPB_CAST_IN)
 #undef SPB_CAST_IN
 #undef SPB_CAST_OUT
+}
+
+int spb_complex_split(int real_dtype, const void* c, int64_t n, void* re, void* im, spb_stream_t stream) {
+    if (n < 0) return SPB_ERR_BAD_ARG;
+    if (n == 0) return SPB_OK;
+    if (!c || !re || !im) return SPB_ERR_BAD_ARG;
+    const unsigned grid = grid_for(n, kMapThreads * 4);
+    if (real_dtype == SPB_F32) complex_split_kernel<float><<<grid, kMapThreads, 0, stream>>>((const float*)c, n, (float*)re, (float*)im);
+    else if (real_dtype == SPB_F64) complex_split_kernel<double><<<grid, kMapThreads, 0, stream>>>((const double*)c, n, (double*)re, (double*)im);
+    else return SPB_ERR_UNSUPPORTED;
+    SPB_LAUNCHED(1);
+    return (int)cudaGetLastError();
+}
+
+int spb_complex_join(int real_dtype, const void* re, const void* im, int64_t n, void* c, spb_stream_t stream) {
+    if (n < 0) return SPB_ERR_BAD_ARG;
+    if (n == 0) return SPB_OK;
+    if (!c || !re || !im) return SPB_ERR_BAD_ARG;
+    const unsigned grid = grid_for(n, kMapThreads * 4);
+    if (real_dtype == SPB_F32) complex_join_kernel<float><<<grid, kMapThreads, 0, stream>>>((const float*)re, (const float*)im, n, (float*)c);
+    else if (real_dtype == SPB_F64) complex_join_kernel<double><<<grid, kMapThreads, 0, stream>>>((const double*)re, (const double*)im, n, (double*)c);
+    else return SPB_ERR_UNSUPPORTED;
+    SPB_LAUNCHED(1);
+    return (int)cudaGetLastError();
 }
 
 int spb_scatter_dense(int dtype, const int64_t* idx, const void* val, int64_t n, void* dense, spb_stream_t stream) {

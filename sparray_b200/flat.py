@@ -46,6 +46,16 @@ _FIXED_POINT_AT_ZERO = ("sin", "tan", "arcsin", "arctan", "sinh", "tanh", "arcsi
                         "expm1", "log1p", "deg2rad", "rad2deg", "floor", "ceil", "trunc", "sqrt")   # compat.py:96-102
 
 
+def _is_complex_data(x):
+    if isinstance(x, torch.Tensor):
+        return x.is_complex()
+    if isinstance(x, np.ndarray):
+        return x.dtype.kind == "c"
+    if isinstance(x, (list, tuple)) and len(x) and isinstance(x[0], (complex, np.complexfloating)):
+        return True
+    return False
+
+
 def _device():
     _k.require_cuda()
     return torch.device("cuda", torch._C._cuda_getDevice())
@@ -91,6 +101,13 @@ class FlatSparray(_BaseSparray):
       self.indices : sorted int64 device tensor of nonzero flat indices
       self.shape : tuple of integers, ala ndarray shape
     """
+
+    def __new__(cls, indices=None, data=None, shape=None, is_canonical=False):
+        # complex values: the subclass that composes every operation from the real kernels (sparray_b200/_complex.py)
+        if cls is FlatSparray and data is not None and _is_complex_data(data):
+            from ._complex import ComplexFlatSparray
+            return object.__new__(ComplexFlatSparray)
+        return object.__new__(cls)
 
     def __init__(self, indices, data, shape=None, is_canonical=False):    # flat.py:27-42
         indices = _to_device(indices, torch.int64)
@@ -176,6 +193,9 @@ class FlatSparray(_BaseSparray):
     def from_ndarray(arr):
         """Converts an array-like (host or device) to a FlatSparray object."""
         shape = tuple(arr.shape) if hasattr(arr, "shape") else np.shape(arr)
+        if _is_complex_data(arr):
+            from ._complex import ComplexFlatSparray
+            return ComplexFlatSparray._from_dense(arr)
         dense = _to_device(arr)
         idx, val = _k.select_nonzero(dense)
         return FlatSparray(idx, val, shape=shape, is_canonical=True)
@@ -517,6 +537,8 @@ class FlatSparray(_BaseSparray):
 
     def __mul__(self, other):                                              # flat.py:507-518
         if _is_scalar(other):
+            if isinstance(other, (complex, np.complexfloating)) and complex(other).imag != 0:
+                return self.astype(np.complex64 if self.dtype == np.float32 else np.complex128) * other
             return self._scalar_map("mul_s", other)
         lhs, rhs = self._handle_broadcasting(other)
         if isinstance(rhs, FlatSparray):
@@ -794,6 +816,10 @@ class FlatSparray(_BaseSparray):
         return NotImplemented
 
     def astype(self, t):
+        if np.dtype(t).kind == "c":
+            from ._complex import ComplexFlatSparray
+            part = self.astype(np.float32 if np.dtype(t) == np.complex64 else np.float64)
+            return ComplexFlatSparray._from_parts(part, part._with_data(torch.zeros_like(part.data)))
         return self._with_data(_k.cast(self.data, dt.torch_dtype(np.dtype(t))))
 
     def conj(self):

@@ -113,6 +113,22 @@ def main():
     add("scalar_eq0", (6, 7), "float64", [], "a == 0")
     add("pow0", (6, 7), "float64", [], "a ** 0")
 
+    # ---- complex values: the reference's own complex test data is ``dense * 1j`` (test_math.py:18-20) --------------
+    cz = ["c = a * 1j"]
+    add("cplx_times_i", (6, 7), "float64", [], "a * 1j")
+    add("cplx_neg", (6, 7), "float64", cz, "-c")
+    add("cplx_conj", (6, 7), "float64", cz, "c.conj()")
+    add("cplx_scalar", (6, 7), "float64", cz, "c * 3")
+    add("cplx_add_real", (6, 7), "float64", cz, "c + b", b_shape=(6, 7))
+    add("cplx_add_cplx", (6, 7), "float64", cz + ["e = b * 1j"], "c + e", b_shape=(6, 7))
+    add("cplx_sub_cplx", (6, 7), "float64", cz + ["e = b * 1j"], "c - e", b_shape=(6, 7))
+    add("cplx_mul_real", (6, 7), "float64", cz, "c * b", b_shape=(6, 7))
+    add("cplx_abs", (6, 7), "float64", cz, "abs(c)")
+    add("cplx_getitem", (6, 7), "float64", cz, "c[2:5, 1::2]")
+    add("cplx_toarray", (6, 7), "float64", cz, "c.toarray()")
+    add("cplx_from_ndarray", (6, 7), "float64", ["d = a.toarray() * (2 - 1j)"], "FlatSparray.from_ndarray(d)")
+    add("cplx_sum", (6, 7), "float64", cz, "np.asarray(c.sum())")
+
     rec.arrays["manifest"] = np.asarray(json.dumps(rec.manifest))
     np.savez_compressed(OUT, **rec.arrays)
     print("wrote %s: %d cases, %.1f KB" % (OUT, len(rec.manifest), os.path.getsize(OUT) / 1024))

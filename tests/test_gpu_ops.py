@@ -283,6 +283,73 @@ def test_conversion_only_dtypes(sp, dtype):
     np.testing.assert_array_equal(to_np(D.data), np.array([7, 4, 4]).astype(dt_))
 
 
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64], ids=lambda d: np.dtype(d).name)
+def test_complex_values(sp, dtype):
+    """complex FlatSparrays are composed from the real kernels on the (re, im) parts (sparray_b200/_complex.py):
+    against numpy on the dense arrays -- the reference's own complex cases are ``dense2d * 1j`` through the
+    element-wise ops (test_math.py:18-20).  Bit-exact where the real formulas are numpy's own (+ - neg conj, products
+    with a real operand, data movement, comparisons); a few ulp for complex x complex (numpy fuses the multiply-adds)
+    and for abs (numpy: hypot)."""
+    rng = np.random.default_rng(11)
+    shape = (13, 9, 7)
+    ct = np.dtype(dtype)
+    ft = np.float32 if ct == np.complex64 else np.float64
+
+    def dense(p=0.3):
+        m = rng.random(shape) < p
+        d = np.zeros(shape, dtype=ct)
+        d[m] = (rng.standard_normal(int(m.sum())) + 1j * rng.standard_normal(int(m.sum()))).astype(ct)
+        d[rng.random(shape) < 0.05] = 2.0               # purely real entries
+        d[rng.random(shape) < 0.05] = -1.5j             # purely imaginary entries
+        return d
+    da, db = dense(), dense()
+    dr = np.where(rng.random(shape) < 0.3, rng.standard_normal(shape), 0).astype(ft)
+    A, B, R = sp.FlatSparray.from_ndarray(da), sp.FlatSparray.from_ndarray(db), sp.FlatSparray.from_ndarray(dr)
+    assert A.dtype == ct and sp.is_sparray(A) and A.nnz == np.count_nonzero(da)
+    np.testing.assert_array_equal(A.toarray(), da)
+    idx, val = A.to_numpy()
+    np.testing.assert_array_equal(val, da.ravel()[idx])
+    for name, got, want in [
+            ("add", A + B, da + db), ("sub", A - B, da - db), ("mul", A * B, da * db),
+            ("add_real", A + R, da + dr), ("radd_real", R + A, dr + da), ("mul_real", A * R, da * dr), ("rmul_real", R * A, dr * da),
+            ("rsub_real", R - A, dr - da), ("neg", -A, -da), ("conj", A.conj(), da.conj()), ("real", A.real, da.real), ("imag", A.imag, da.imag),
+            ("scalar_real", A * 2.5, da * ft(2.5)), ("scalar_cplx", A * (1 - 2j), da * ct.type(1 - 2j)), ("real_times_cplx", R * 2j, dr * ct.type(2j)),
+            ("transpose", A.transpose(2, 0, 1), da.transpose(2, 0, 1)), ("T", A.T, da.T),
+            ("row", A[3], da[3]), ("box", A[2:11:3, :, 1:6], da[2:11:3, :, 1:6]),
+            ("reshape", A.reshape((13 * 9, 7)), da.reshape(13 * 9, 7)), ("astype", A.astype(np.complex128), da.astype(np.complex128)),
+            ("ne", A != B, da != db), ("pow2", A ** 2, da * da), ("to_complex", R.astype(ct), dr.astype(ct))]:
+        g = got.toarray()
+        assert g.dtype == want.dtype, (name, g.dtype, want.dtype)
+        if name in ("mul", "scalar_cplx", "pow2"):
+            # complex x complex: numpy's SIMD loops fuse the multiply-adds (fmaddsub), which no composition of
+            # separately rounded products reproduces bit for bit -- and which depends on the CPU numpy runs on
+            np.testing.assert_allclose(g, want, rtol=4 * np.finfo(ft).eps, atol=4 * np.finfo(ft).eps, err_msg=name)
+        else:
+            np.testing.assert_array_equal(g, want, err_msg=name)
+    np.testing.assert_allclose(abs(A).toarray(), np.abs(da), rtol=1e-6 if ct == np.complex64 else 1e-14)
+    np.testing.assert_allclose((A / 4).toarray(), da / 4, rtol=1e-6 if ct == np.complex64 else 1e-15)
+    np.testing.assert_allclose(A.sum(), da.sum(), rtol=1e-5 if ct == np.complex64 else 1e-12)
+    assert A[3, 2, 1] == da[3, 2, 1] and A[0, 0, 0] == da[0, 0, 0]
+    # (A == B) on the union of the stored elements
+    eq = (A == A.copy())
+    assert eq.dtype == np.bool_ and bool(to_np(eq.data).all())
+    C = A.copy()
+    C[1, 2, 3] = 3 - 4j
+    C[:, 1, 0] = 1j
+    want = da.copy()
+    want[1, 2, 3] = 3 - 4j
+    want[:, 1, 0] = 1j
+    np.testing.assert_array_equal(C.toarray(), want)
+    # non-canonical ctor: duplicates are summed
+    D = sp.FlatSparray(np.array([5, 3, 5, 9], dtype=np.int64), np.array([1 + 1j, 2, 3 - 2j, 4j], dtype=ct), shape=(12,))
+    np.testing.assert_array_equal(to_np(D.indices), [3, 5, 9])
+    np.testing.assert_array_equal(to_np(D.data), np.array([2, 4 - 1j, 4j], dtype=ct))
+    # what cannot be composed from the real kernels is refused loudly, as is what the reference refuses
+    for bad in (lambda: A.sum(axis=0), lambda: A < B, lambda: A.sin(), lambda: A.dot(np.ones(7)), lambda: A + 1, lambda: A.max()):
+        with pytest.raises(TypeError):
+            bad()
+
+
 def test_config2_chain(sp):
     """BASELINE config 2 at full size: c = a*b (intersection) then c.sum(axis=2); also a.sum(axis=2)."""
     shape = (256, 256, 256, 64)
