@@ -569,6 +569,7 @@ def sharded_exchange(torch, dist, A, B, rank, world, barrier, max_over_ranks):
     # the same product with no exchange step: b's shards published in symmetric memory (untimed, once per
     # operand), the merge kernels read the partner's slices over NVLink inside their TMA staging
     t_peer, peer_note = None, "ok"
+    t_pull = t_pull_mul = None
     try:
         b_pub = b_sh.publish()
         want = (a_sh * b_sh)
@@ -580,6 +581,15 @@ def sharded_exchange(torch, dist, A, B, rank, world, barrier, max_over_ranks):
             t_peer = timed(lambda: a_sh.binop_peer(b_pub, "intersect", "mul").nnz_local)
         else:
             peer_note = "MISMATCH against the repartition path"
+        # the repartition itself, PULLED from the published shards (peer copies over NVLink, no NCCL send / recv)
+        pulled = b_pub.repartition(even, b_sh.ops)
+        ref = b_sh.repartition(even)
+        if bool((pulled.indices == ref.indices).all()) and bool((pulled.data == ref.data).all()):
+            t_pull = timed(lambda: b_pub.repartition(even, b_sh.ops))
+            t_pull_mul = timed(lambda: (a_sh * b_pub.repartition(even, b_sh.ops)).nnz_local)
+        else:
+            peer_note = "MISMATCH of the pulled repartition"
+        del pulled, ref
         b_pub.barrier()
     except Exception as exc:      # symmetric memory unavailable on this box: the NCCL path above still stands
         peer_note = "unavailable: %s" % str(exc).splitlines()[0][:200]
@@ -594,8 +604,12 @@ def sharded_exchange(torch, dist, A, B, rank, world, barrier, max_over_ranks):
             "elements_repartitioned": n_all,
             "elements_crossing_gpus": sent_all,
             "nvlink_GBps_per_gpu_send": sent_all / world * bytes_per_elem / (t_rep * 1e-3) / 1e9,
+            "repartition_pulled_ms": t_pull, "mul_with_pulled_repartition_ms": t_pull_mul,
+            "nvlink_GBps_per_gpu_pulled": (sent_all / world * bytes_per_elem / (t_pull * 1e-3) / 1e9) if t_pull else None,
             "nvlink_peak_GBps_per_direction": 900.0,
-            "note": "repartition = lower_bound of the splitters, counts all-gather (host sync), index and value "
+            "note": "repartition_pulled = PeerShards.repartition: every rank copies its slices straight out of its peers' "
+                    "published shards (symmetric memory, device copies over NVLink; one all-gather of cut positions).  "
+                    "repartition = lower_bound of the splitters, counts all-gather (host sync), index and value "
                     "all_to_all_single (NCCL); received segments are already in order, no merge.  peer loads = "
                     "ShardedFlatSparray.binop_peer: one all-gather of cut positions, then one fused merge launch "
                     "per overlapping source rank reading that rank's slice from symmetric memory over NVLink"}
@@ -671,6 +685,11 @@ def config4_union(sp, torch, dist, rank, world, barrier, max_over_ranks, peak):
             b_pub = B_sh.publish()
             t_peer = timed(lambda: A.binop_peer(b_pub, "union", "add").nnz_local, reps=3, warm=1)
             extra["misaligned_b"]["add_with_peer_loads_ms"] = t_peer
+            t_pull = timed(lambda: b_pub.repartition(cuts, B_sh.ops), reps=3, warm=1)
+            t_pull_add = timed(lambda: (A + b_pub.repartition(cuts, B_sh.ops)).nnz_local, reps=3, warm=1)
+            extra["misaligned_b"]["repartition_pulled_ms"] = t_pull
+            extra["misaligned_b"]["add_with_pulled_repartition_ms"] = t_pull_add
+            extra["misaligned_b"]["nvlink_GBps_per_gpu_pulled"] = int(mv.item()) / world * 12 / (t_pull * 1e-3) / 1e9
             b_pub.barrier()
         except Exception as exc:
             extra["misaligned_b"]["peer_loads"] = "unavailable: %s" % str(exc).splitlines()[0][:200]

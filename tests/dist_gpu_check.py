@@ -54,10 +54,18 @@ def main():
     # the same misaligned binops with NO exchange step: B's shards in symmetric memory, the merge
     # kernels read the partner's slices over NVLink
     Bp = B.publish()
+    # the pulled repartition (peer copies over NVLink) against the NCCL one
+    for target in (A.splitters, sp, odd):
+        got, want = Bp.repartition(target, B.ops), B.repartition(target)
+        assert got.splitters == want.splitters
+        assert torch.equal(got.indices, want.indices) and torch.equal(got.data, want.data), "pulled repartition differs"
     for X in (A, A2):
         same(X.binop_peer(Bp, "union", "add"), fo.pairwise_union(ai, av, bi, bv, np.add))
         same(X.binop_peer(Bp, "intersect", "mul"), fo.pairwise_intersect(ai, av, bi, bv, np.multiply))
         same(X.binop_peer(Bp, "union", "sub"), fo.pairwise_union(ai, av, bi, -bv, np.add))
+        # a published operand handed to the ordinary operators: pulled repartition + local merge
+        same(X + Bp, fo.pairwise_union(ai, av, bi, bv, np.add))
+        same(X * Bp, fo.pairwise_intersect(ai, av, bi, bv, np.multiply))
     Bp.barrier()
     for axis in range(4):
         S = A2.sum(axis)
