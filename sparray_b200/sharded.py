@@ -456,6 +456,16 @@ def _merge_runs(ops, keys, vals, counts, op):
     return runs[0]
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 class PeerShards:
     """A range-sharded operand whose shards live in symmetric memory: every rank can hand slices of
     ANY rank's shard to a local kernel as ordinary device pointers (peer mappings over NVLink /
@@ -511,12 +521,20 @@ class PeerShards:
             offs.append(offs[-1] + c)
         recv_idx = torch.empty(offs[-1], dtype=torch.int64, device=dev)
         recv_val = torch.empty(offs[-1], dtype=self.dtype, device=dev)
+        cur = torch.cuda.current_stream()
+        side = _side_stream(dev)
+        side.wait_stream(cur)
         for k in range(self.world):
             s = (self.rank + 1 + k) % self.world
             if counts[s]:
                 src_idx, src_val = self.slice_of(s, cuts[s][self.rank], cuts[s][self.rank + 1])
-                recv_idx[offs[s]:offs[s + 1]].copy_(src_idx)
-                recv_val[offs[s]:offs[s + 1]].copy_(src_val)
+                # my own slice is an HBM-to-HBM copy: it runs beside the NVLink pulls, on a second stream
+                with torch.cuda.stream(side if s == self.rank else cur):
+                    recv_idx[offs[s]:offs[s + 1]].copy_(src_idx)
+                    recv_val[offs[s]:offs[s + 1]].copy_(src_val)
+        recv_idx.record_stream(side)
+        recv_val.record_stream(side)
+        cur.wait_stream(side)
         return ShardedFlatSparray(recv_idx, recv_val, self.shape, new_splitters, self.group, ops)
 
     def slice_of(self, src, c0, c1):
