@@ -205,8 +205,8 @@ class ShardedFlatSparray:
     def _binop(self, other, kind, op):
         assert self.shape == other.shape
         if isinstance(other, PeerShards):
-            # a published operand: its slices are pulled out of the peers' memory over NVLink (492 GB/s per GPU at
-            # BASELINE config 5's size on 8 GPUs, against 232 GB/s for the NCCL send / receive group below)
+            # a published operand: its slices are pulled out of the peers' memory over NVLink (526 GB/s per GPU at
+            # BASELINE config 5's size on 8 GPUs, against 236 GB/s for the NCCL send / receive group below)
             other = other.repartition(self.splitters, self.ops)
         elif other.splitters != self.splitters:
             other = other.repartition(self.splitters)       # the only communication of a binop
