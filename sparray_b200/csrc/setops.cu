@@ -301,7 +301,20 @@ struct Layout {
 
 template <typename V, typename VO, int KIND, bool HAS_VAL, bool SEAM>
 struct Cfg {
-    static constexpr int kVT = KIND == KIND_UNION ? 8 : 12;
+#ifndef SPB_UNION_VT4
+#define SPB_UNION_VT4 8
+#endif
+#ifndef SPB_UNION_VT8
+#define SPB_UNION_VT8 8
+#endif
+#ifndef SPB_UNION_CTAS4
+#define SPB_UNION_CTAS4 6
+#endif
+#ifndef SPB_UNION_CTAS8
+#define SPB_UNION_CTAS8 5
+#endif
+    static constexpr bool kWideOut = HAS_VAL && sizeof(VO) == 8;
+    static constexpr int kVT = KIND == KIND_UNION ? (kWideOut ? SPB_UNION_VT8 : SPB_UNION_VT4) : 12;
     static constexpr int kTile = kNT * kVT;
     static constexpr int kFixedSlots = 8 * kVT;                          // private output slots per tile (intersections)
     static constexpr int kCap = KIND == KIND_UNION ? kTile : kTile / 2;  // outputs per tile, at most
@@ -311,7 +324,7 @@ struct Cfg {
     // no merging warp is held up by the L2 round trips
     static constexpr int kHelperWarp = KIND == KIND_UNION ? kNT / 32 : 0;
     static constexpr int kThreads = KIND == KIND_UNION ? kNT + 32 : kNT;
-    static constexpr int kMinCtas = KIND == KIND_INTERSECT ? 8 : ((HAS_VAL && sizeof(VO) == 8) ? 5 : 6);   // what shared memory allows
+    static constexpr int kMinCtas = KIND == KIND_INTERSECT ? 8 : (kWideOut ? SPB_UNION_CTAS8 : SPB_UNION_CTAS4);   // what shared memory allows
     // unions stage their output keys as 32-bit tile-local offsets (tiles spanning >= 2^32 store directly);
     // input values are never staged: every one is read exactly once, straight from global memory
     using L = Layout<kVT, KIND == KIND_INTERSECT ? 0 : kCap * 4, kPayload>;
