@@ -302,16 +302,16 @@ struct Layout {
 template <typename V, typename VO, int KIND, bool HAS_VAL, bool SEAM>
 struct Cfg {
 #ifndef SPB_UNION_VT4
-#define SPB_UNION_VT4 8
+#define SPB_UNION_VT4 10
 #endif
 #ifndef SPB_UNION_VT8
-#define SPB_UNION_VT8 8
+#define SPB_UNION_VT8 6
 #endif
 #ifndef SPB_UNION_CTAS4
-#define SPB_UNION_CTAS4 6
+#define SPB_UNION_CTAS4 5
 #endif
 #ifndef SPB_UNION_CTAS8
-#define SPB_UNION_CTAS8 5
+#define SPB_UNION_CTAS8 6
 #endif
     static constexpr bool kWideOut = HAS_VAL && sizeof(VO) == 8;
     static constexpr int kVT = KIND == KIND_UNION ? (kWideOut ? SPB_UNION_VT8 : SPB_UNION_VT4) : 12;
