@@ -120,11 +120,12 @@ struct SetopParams {
 
 enum { KIND_UNION = 0, KIND_INTERSECT = 1 };
 
-constexpr int kNT = 256;   // threads per CTA
-// merged items per thread: 12 for intersections (outputs are rare and go straight to global memory, so
-// a 3072-item tile of keys is all the shared memory a CTA needs: 8 CTAs per SM, and the per-thread
-// merge-path search is amortised over more items), 8 for unions (a full tile of outputs is staged)
-constexpr int key_region_bytes(int vt) { return (kNT * vt + 4) * 8 + 128 + vt * 8; }
+// Tile shapes (struct Cfg below).  Intersections: 128 merging threads x 24 items -- outputs are rare and go
+// straight to global memory, so a 3072-item tile of keys is all the shared memory a CTA needs (8 CTAs per
+// SM), and a thread's 12-round merge-path search is paid once per 24 items (256 x 12 measured 62.6 us per
+// config-2 call, 128 x 24 58.9).  Unions stage a full tile of outputs: 256 threads x 10 (4-byte results) or
+// x 6 (8-byte results).
+constexpr int key_region_bytes(int nt, int vt) { return ((nt * vt + 4) * 8 + 128 + vt * 8 + 15) & ~15; }
 
 // ---- launch 1: merge-path split of every tile + its staging descriptor ------------------------
 // Half-warps search the tile diagonals (16-ary, bracketed around the proportional guess); one thread
@@ -288,11 +289,11 @@ struct Geom {            // where a staged tile lives inside its buffer
     int offA, offB;      // byte offset of As64[0] / Bs64[0] from the buffer start
 };
 
-template <int VT, int OUT_KEYS, int OUT_PAYLOAD>   // items/thread; staging bytes (keys, values / lut)
+template <int NT, int VT, int OUT_KEYS, int OUT_PAYLOAD>   // merging threads; items/thread; staging bytes (keys, values / lut)
 struct Layout {
-    static constexpr int kTile = kNT * VT;
+    static constexpr int kTile = NT * VT;
     static constexpr int kHeader = 256;
-    static constexpr int kBuf = key_region_bytes(VT);                    // the staged input keys of one tile
+    static constexpr int kBuf = key_region_bytes(NT, VT);                   // the staged input keys of one tile
     static constexpr int kStgKeys = OUT_KEYS;                            // compacted outputs waiting for their offset
     static constexpr int kStg = ((OUT_KEYS + OUT_PAYLOAD) + 15) & ~15;
     static constexpr int kTotal = kHeader + kBuf + kStg;
@@ -301,6 +302,18 @@ struct Layout {
 
 template <typename V, typename VO, int KIND, bool HAS_VAL, bool SEAM>
 struct Cfg {
+#ifndef SPB_UNION_NT
+#define SPB_UNION_NT 256
+#endif
+#ifndef SPB_ISECT_NT
+#define SPB_ISECT_NT 128
+#endif
+#ifndef SPB_ISECT_VT
+#define SPB_ISECT_VT 24
+#endif
+#ifndef SPB_ISECT_CTAS
+#define SPB_ISECT_CTAS 8
+#endif
 #ifndef SPB_UNION_VT4
 #define SPB_UNION_VT4 10
 #endif
@@ -314,20 +327,22 @@ struct Cfg {
 #define SPB_UNION_CTAS8 6
 #endif
     static constexpr bool kWideOut = HAS_VAL && sizeof(VO) == 8;
-    static constexpr int kVT = KIND == KIND_UNION ? (kWideOut ? SPB_UNION_VT8 : SPB_UNION_VT4) : 12;
-    static constexpr int kTile = kNT * kVT;
-    static constexpr int kFixedSlots = 8 * kVT;                          // private output slots per tile (intersections)
+    // merging threads per CTA and items per thread (a thread's 12-round merge-path search is paid once per kVT items)
+    static constexpr int kNTc = KIND == KIND_UNION ? SPB_UNION_NT : SPB_ISECT_NT;
+    static constexpr int kVT = KIND == KIND_UNION ? (kWideOut ? SPB_UNION_VT8 : SPB_UNION_VT4) : SPB_ISECT_VT;
+    static constexpr int kTile = kNTc * kVT;
+    static constexpr int kFixedSlots = kTile / 32;                       // private output slots per tile (intersections)
     static constexpr int kCap = KIND == KIND_UNION ? kTile : kTile / 2;  // outputs per tile, at most
     static constexpr int kPayload = KIND == KIND_INTERSECT ? 0
                                     : (HAS_VAL ? kCap * (int)sizeof(VO) : (SEAM ? kCap : 0));
     // unions resolve their output offset by look-back: a ninth warp does it (and the staging) so that
     // no merging warp is held up by the L2 round trips
-    static constexpr int kHelperWarp = KIND == KIND_UNION ? kNT / 32 : 0;
-    static constexpr int kThreads = KIND == KIND_UNION ? kNT + 32 : kNT;
-    static constexpr int kMinCtas = KIND == KIND_INTERSECT ? 8 : (kWideOut ? SPB_UNION_CTAS8 : SPB_UNION_CTAS4);   // what shared memory allows
+    static constexpr int kHelperWarp = KIND == KIND_UNION ? kNTc / 32 : 0;
+    static constexpr int kThreads = KIND == KIND_UNION ? kNTc + 32 : kNTc;
+    static constexpr int kMinCtas = KIND == KIND_INTERSECT ? SPB_ISECT_CTAS : (kWideOut ? SPB_UNION_CTAS8 : SPB_UNION_CTAS4);   // what shared memory allows
     // unions stage their output keys as 32-bit tile-local offsets (tiles spanning >= 2^32 store directly);
     // input values are never staged: every one is read exactly once, straight from global memory
-    using L = Layout<kVT, KIND == KIND_INTERSECT ? 0 : kCap * 4, kPayload>;
+    using L = Layout<kNTc, kVT, KIND == KIND_INTERSECT ? 0 : kCap * 4, kPayload>;
 };
 
 struct EdgeReg {         // an unaligned head / tail key riding in a register until its buffer is live
@@ -431,7 +446,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // barrier among the merging warps only (unions have a ninth helper warp that must not be waited for)
 template <int KIND>
 __device__ __forceinline__ void sync_mergers() {
-    if constexpr (KIND == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+    if constexpr (KIND == 0) asm volatile("bar.sync 1, %0;" ::"n"(SPB_UNION_NT) : "memory");
     else __syncthreads();
 }
 
@@ -578,11 +593,11 @@ setop_kernel(const SetopParams p) {
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
-    if (lane == 31 && warp < kNT / 32) warp_sums[warp] = incl;
+    if (lane == 31 && warp < C::kNTc / 32) warp_sums[warp] = incl;
     sync_mergers<KIND>();                                              // (C)
     int wofs = 0, tile_total = 0;
 #pragma unroll
-    for (int w = 0; w < kNT / 32; ++w) {
+    for (int w = 0; w < C::kNTc / 32; ++w) {
         const int s = warp_sums[w];
         if (w < warp) wofs += s;
         tile_total += s;
@@ -706,7 +721,7 @@ setop_kernel(const SetopParams p) {
             sync_mergers<KIND>();                                      // (D) staging complete
             mbar_wait(ready_bar, 0);                                   // offset resolved by the helper warp
             const int64_t base = *base_s;
-            for (int i = tid; i < tile_total; i += kNT) {
+            for (int i = tid; i < tile_total; i += C::kNTc) {
                 p.out_idx[base + i] = kbase + (int64_t)skey[i];
                 if constexpr (HAS_VAL) o_val[base + i] = sval[i];
                 if constexpr (SEAM) {
