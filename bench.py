@@ -49,7 +49,7 @@ DTYPE = np.float32
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # ncu --set full capture of this workload (profiles/README.md); None until a capture exists
-NCU_TRAFFIC_BYTES = 213624832   # partition 6.88 MB + merge 195.89 MB read, 7.12 MB written + reorder 3.73 MB
+NCU_TRAFFIC_BYTES = 210896384   # partition 6.88 MB + merge 195.89 MB read, 4.39 MB written + reorder 3.73 MB
 NCU_TRAFFIC_SOURCE = ("profiles/r2_setops_ncu_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum of the three launches of one "
                       "spb_intersect_binop call (merge_partition_kernel, setop_kernel<float,float,INTERSECT>, merge_reorder_kernel) "
                       "at this workload, ncu --set full")
