@@ -471,12 +471,96 @@ __global__ void __launch_bounds__(256) spmv_rows_kernel(const int64_t* __restric
     }
 }
 
+// Variant for LONG rows (>= 8 stored elements per row on average): a lane owns kSpmvRun CONSECUTIVE elements
+// (one sector of indices, one of float64 values), multiplies them by their gathered x (kSpmvRun independent
+// gathers in flight per lane) and adds up those of its first row; a lane whose elements all lie in one row --
+// the usual case -- hands (row, sum) to ONE segmented shuffle scan per 32 * kSpmvRun elements, a lane that
+// straddles rows adds its pieces atomically on its own.
+constexpr int kSpmvRun = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256) spmv_runs_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
+                                                        int64_t n, const FastDiv div, const T* __restrict__ x,
+                                                        double* __restrict__ y, const int64_t nrows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t chunk = 32 * kSpmvRun;
+    for (int64_t base = warp_global * chunk; base < n; base += nwarps * chunk) {
+        const int64_t i0 = base + (int64_t)lane * kSpmvRun;
+        int64_t key[kSpmvRun];
+        T v[kSpmvRun];
+#pragma unroll
+        for (int j = 0; j < kSpmvRun; ++j) {
+            key[j] = i0 + j < n ? __ldcs(idx + i0 + j) : -1;
+            v[j] = i0 + j < n ? __ldcs(val + i0 + j) : T(0);
+        }
+        int64_t row[kSpmvRun];
+        double prod[kSpmvRun];
+#pragma unroll
+        for (int j = 0; j < kSpmvRun; ++j) {
+            row[j] = -1;
+            prod[j] = 0.0;
+            if (key[j] >= 0) {
+                const int64_t r = (int64_t)fastdiv((uint64_t)key[j], div);
+                const int64_t col = key[j] - r * (int64_t)div.d;
+                prod[j] = (double)v[j] * (double)__ldg(x + col);
+                row[j] = r < nrows ? r : -1;        // rows beyond the shape (resize()) must not touch y
+            }
+        }
+        bool single = row[0] >= 0;
+#pragma unroll
+        for (int j = 1; j < kSpmvRun; ++j) single = single && row[j] == row[0];
+        int64_t cell = -2 - lane;                   // negative and distinct: takes no part in the warp's runs
+        double s = 0.0;
+        if (single) {
+            cell = row[0];
+            s = (prod[0] + prod[1]) + (prod[2] + prod[3]);
+        } else {
+            int64_t run = -1;
+            double rs = 0.0;
+#pragma unroll
+            for (int j = 0; j < kSpmvRun; ++j) {
+                if (row[j] >= 0) {
+                    if (row[j] != run) {
+                        if (run >= 0) atomicAdd(y + run, rs);
+                        run = row[j];
+                        rs = prod[j];
+                    } else {
+                        rs += prod[j];
+                    }
+                }
+            }
+            if (run >= 0) atomicAdd(y + run, rs);
+        }
+        const int64_t cprev = __shfl_up_sync(0xffffffffu, cell, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || cprev != cell || cell < 0);
+        const int start = 31 - __clz(heads & ((2u << lane) - 1u));       // first lane of my run
+        if (heads != 0xffffffffu) {                                       // some run is longer than one lane
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane - o >= start) s += up;
+            }
+        }
+        const bool last = lane == 31 || ((heads >> (lane + 1)) & 1u);
+        if (cell >= 0 && last) atomicAdd(y + cell, s);
+    }
+}
+static_assert(kSpmvRun == 4, "the single-run sum above is written out for 4 elements");
+
 template <typename T>
 int launch_spmv_rows(const int64_t* idx, const void* vals, int64_t n, int64_t ncols, int64_t nrows, const void* x,
                      double* y, cudaStream_t stream) {
     int64_t blocks = ceil_div(n, 256 * kSpmvUnroll);
     const int64_t cap = (int64_t)device_sm_count() * 16;
     if (blocks > cap) blocks = cap;
+    if (n >= 8 * nrows) {                           // long rows: one segmented scan per 128 elements
+        spmv_runs_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(idx, (const T*)vals, n, make_fastdiv((uint64_t)ncols),
+                                                                 (const T*)x, y, nrows);
+        SPB_LAUNCHED(1);
+        return (int)cudaGetLastError();
+    }
     spmv_rows_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(idx, (const T*)vals, n, make_fastdiv((uint64_t)ncols),
                                                              (const T*)x, y, nrows);
     SPB_LAUNCHED(1);
