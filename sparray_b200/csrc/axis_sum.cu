@@ -218,6 +218,141 @@ __global__ void __launch_bounds__(256) axis_accumulate_runs_kernel(const int64_t
     }
 }
 
+// The same for the plain case -- the LAST axis group is summed and every other group keeps its place, so the
+// cell of an element is its flat index divided by the size of that group and nothing else: a lane's four
+// ascending elements need TWO divisions (first and last element; equal quotients = one run, the usual case),
+// a lane that straddles a group boundary places its middle elements by comparing them with the two group
+// bounds.  Full chunks are read with 128-bit loads.  (The general kernel above re-keys every element: 116
+// thread instructions per element, 80 % issue activity on the config-4 row sums -- it was bound by that.)
+template <typename T, int BYTES = (int)sizeof(T)>
+struct Load4;
+template <typename T>
+struct Load4<T, 8> {
+    static __device__ __forceinline__ void run(const T* p, T (&o)[4]) {
+        const ulonglong2 a = __ldcs(reinterpret_cast<const ulonglong2*>(p));
+        const ulonglong2 b = __ldcs(reinterpret_cast<const ulonglong2*>(p) + 1);
+        const unsigned long long w[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) memcpy(&o[j], &w[j], 8);
+    }
+};
+template <typename T>
+struct Load4<T, 4> {
+    static __device__ __forceinline__ void run(const T* p, T (&o)[4]) {
+        const uint4 a = __ldcs(reinterpret_cast<const uint4*>(p));
+        const unsigned w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) memcpy(&o[j], &w[j], 4);
+    }
+};
+template <typename T>
+struct Load4<T, 2> {
+    static __device__ __forceinline__ void run(const T* p, T (&o)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = __ldcs(p + j);
+    }
+};
+template <typename T>
+struct Load4<T, 1> {
+    static __device__ __forceinline__ void run(const T* p, T (&o)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = __ldcs(p + j);
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) axis_accumulate_lastaxis_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
+                                                                   int64_t n, const int64_t* __restrict__ n_dev,
+                                                                   const FastDiv dv, double* __restrict__ acc,
+                                                                   uint8_t* __restrict__ touched, const int64_t cell_lo,
+                                                                   const int64_t cells, uint64_t* __restrict__ clear_state,
+                                                                   const int64_t clear_n, const int aligned) {
+    static_assert(kAccItems == 4, "written out for 4 elements per lane");
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();   // operands (and n_dev) may come from the previous launch
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < clear_n; i += (int64_t)gridDim.x * blockDim.x)
+        clear_state[i] = 0;
+    if (n_dev) {                       // the producer's count never left the device; n is its upper bound
+        const int64_t m = *n_dev;
+        n = m < n ? m : n;
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t chunk = 32 * kAccItems;
+    auto add_run = [&](uint64_t g, double rs) {      // one run's sum into its cell, if the cell is in the window
+        const uint64_t c = g - (uint64_t)cell_lo;
+        if (c < (uint64_t)cells) {
+            atomicAdd(acc + c, rs);
+            if (touched) touched[c] = 1;             // a flag per cell: explicit zeros survive
+        }
+    };
+    for (int64_t base = warp_global * chunk; base < n; base += nwarps * chunk) {
+        const int64_t i0 = base + (int64_t)lane * kAccItems;
+        int64_t key[kAccItems];
+        T tv[kAccItems];
+        if (aligned && base + chunk <= n) {          // (uniform) a full chunk: two 128-bit loads of indices
+            Load4<int64_t>::run(idx + i0, key);
+            Load4<T>::run(val + i0, tv);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kAccItems; ++j) {
+                key[j] = i0 + j < n ? __ldcs(idx + i0 + j) : -1;
+                tv[j] = i0 + j < n ? __ldcs(val + i0 + j) : T(0);
+            }
+        }
+        double v[kAccItems];
+#pragma unroll
+        for (int j = 0; j < kAccItems; ++j) v[j] = (double)tv[j] + 0.0;       // (-0.0 goes in as +0.0)
+        int64_t cell = -2 - lane;      // negative and distinct: takes no part in the warp's runs
+        double s = 0.0;
+        if (key[0] >= 0) {
+            // elements ascend and the missing ones (-1, past the end) are the last: the last real one
+            int jl = 3;
+#pragma unroll
+            for (int j = 3; j > 0; --j)
+                if (key[j] < 0) jl = j - 1;
+            const uint64_t g0 = fastdiv((uint64_t)key[0], dv);
+            const uint64_t gl = jl == 0 ? g0 : fastdiv((uint64_t)key[jl], dv);
+            if (g0 == gl) {            // one run (all four elements, or the real ones of the last chunk)
+                const uint64_t c = g0 - (uint64_t)cell_lo;
+                if (c < (uint64_t)cells) {
+                    cell = (int64_t)c;
+                    s = (v[0] + v[1]) + (v[2] + v[3]);
+                }
+            } else {
+                // several runs: each goes in atomically right here.  A middle element lies in the first group
+                // (below its end), in the last one (at or above its start), or -- a lane spanning three groups
+                // or more, rare -- somewhere in between
+                const uint64_t end0 = (g0 + 1) * dv.d, startl = gl * dv.d;
+                uint64_t run = g0;
+                double rs = v[0];
+#pragma unroll
+                for (int j = 1; j < kAccItems; ++j) {
+                    if (j <= jl) {
+                        const uint64_t k = (uint64_t)key[j];
+                        const uint64_t g = k < end0 ? g0 : (k >= startl ? gl : fastdiv(k, dv));
+                        if (g != run) {
+                            add_run(run, rs);
+                            run = g;
+                            rs = v[j];
+                        } else {
+                            rs += v[j];
+                        }
+                    }
+                }
+                add_run(run, rs);
+            }
+        }
+        bool last;
+        s = warp_run_sum(cell, s, lane, last);
+        if (cell >= 0 && last) {
+            atomicAdd(acc + cell, s);
+            if (touched) touched[cell] = 1;
+        }
+    }
+}
+
 // Emits the touched cells in key order and puts every cell it emitted back to zero, so the
 // accumulator slab is all-zero again when the call is over (no memset per call).  One thread owns
 // kSelCells cells (one 16-byte load of flag bytes); a tile of 256 threads covers 4 K cells -- thousands of
@@ -372,8 +507,20 @@ static int launch_accumulate(int dtype, const int64_t* idx, const void* val, int
     // that pre-reduces inside a lane and scans once per 128 elements
     const bool runs = rk.ndim >= 1 && rk.out_mul[rk.ndim - 1] == 0;      // the finest axis group is reduced
     const bool long_runs = runs && n >= 8 * cells;
+    // plain last-axis sum: every kept group keeps its place, so cell == flat index / size of the last group
+    bool plain = long_runs && rk.ndim >= 2;
+    if (plain) {
+        const uint64_t inner = rk.in_div[rk.ndim - 2].d;
+        for (int ax = 0; ax < rk.ndim - 1; ++ax)
+            if ((uint64_t)rk.out_mul[ax] * inner != rk.in_div[ax].d) plain = false;
+    }
+    const int aligned = ((reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(val)) & 15) == 0;
 #define SPB_ACC(T)                                                                                            \
-    if (long_runs) {                                                                                          \
+    if (plain) {                                                                                              \
+        SPB_CUDA_TRY(launch_pdl(axis_accumulate_lastaxis_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, \
+                                idx, (const T*)val, n, n_dev, rk.in_div[rk.ndim - 2], acc, touched, cell_lo, cells, \
+                                clear_state, clear_n, aligned));                                              \
+    } else if (long_runs) {                                                                                          \
         SPB_CUDA_TRY(launch_pdl(axis_accumulate_runs_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, \
                                 idx, (const T*)val, n, n_dev, rk, acc, touched, cell_lo, cells, clear_state, clear_n)); \
     } else if (runs) {                                                                                        \
