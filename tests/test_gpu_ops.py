@@ -131,6 +131,54 @@ def test_sum_axis_long_segments(sp):
     assert_sparse_same(A.sum(axis=1), fo.sum_axis(idx, val, shape, 1), exact=False, rtol=1e-5)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64, np.int32, np.int16, np.int8],
+                         ids=lambda d: np.dtype(d).name)
+def test_last_axis_sum_and_spmv_long_rows_edge_cases(sp, dtype):
+    """The long-run kernels (a lane owns four consecutive elements; csrc/axis_sum.cu
+    axis_accumulate_lastaxis_kernel, csrc/reduce.cu spmv_runs_kernel): rows that start and end inside a
+    lane, lanes that span three rows (1-element rows between long ones), a ragged last chunk, operands
+    that are views at an odd element offset (no 128-bit loads), indices past prod(shape) after resize()."""
+    import torch
+    rng = np.random.default_rng(21)
+    ncols = 1000
+    # row lengths: long rows with single-element and empty rows sprinkled in
+    lens = rng.integers(60, 200, size=400)
+    lens[rng.random(400) < 0.15] = 1
+    lens[rng.random(400) < 0.05] = 0
+    lens[5:9] = [1, 1, 2, 1]                                   # a lane spanning several rows
+    rows = np.repeat(np.arange(400), lens)
+    cols = np.concatenate([np.sort(rng.choice(ncols, size=k, replace=False)) for k in lens]) if len(rows) else rows
+    idx = (rows * ncols + cols).astype(np.int64)
+    n = len(idx)
+    assert n >= 8 * 400
+    val = (rng.integers(-50, 50, size=n) if np.dtype(dtype).kind == "i" else rng.standard_normal(n)).astype(dtype)
+    rtol = 1e-5 if np.dtype(dtype) == np.float32 else 1e-12
+    shape = (400, ncols)
+    x = rng.standard_normal(ncols)
+    for cut in (0, 1, 2, 3, 5):                                # views: odd offsets, ragged tails
+        i_t = torch.from_numpy(idx).cuda()[cut:]
+        v_t = torch.from_numpy(val).cuda()[cut:]
+        A = sp.FlatSparray(i_t, v_t, shape=shape, is_canonical=True)
+        want = fo.sum_axis(idx[cut:], val[cut:], shape, 1)
+        assert_sparse_same(A.sum(axis=1), want, exact=False, rtol=rtol)
+        if np.dtype(dtype).kind == "f":
+            xx = x.astype(dtype)
+            got = A.dot(xx)
+            ref = fo.dot_dense_vector(idx[cut:], val[cut:], shape, xx)
+            np.testing.assert_allclose(got, ref, rtol=rtol, atol=rtol * np.abs(ref).max())
+    # a 3-D array: the two leading axes keep their place, the last one is summed
+    shape3 = (20, 20, ncols)
+    A = sp.FlatSparray(torch.from_numpy(idx).cuda(), torch.from_numpy(val).cuda(), shape=shape3, is_canonical=True)
+    assert_sparse_same(A.sum(axis=2), fo.sum_axis(idx, val, shape3, 2), exact=False, rtol=rtol)
+    # stored indices past prod(shape) (resize() allows them): they must not touch anything
+    A = sp.FlatSparray(torch.from_numpy(idx).cuda(), torch.from_numpy(val).cuda(), shape=shape, is_canonical=True)
+    A.resize((300, ncols))
+    keep = idx < 300 * ncols
+    got = A.sum(axis=1)
+    want = fo.sum_axis(idx[keep], val[keep], (300, ncols), 1)
+    assert_sparse_same(got, want, exact=False, rtol=rtol)
+
+
 SLAB_CASES = [
     # shape, nnz, axes: multi-tile runs of the one-pass slab kernel (csrc/slab_sum.cu)
     ((64, 48, 40, 16), 400_000, (3, 2, 1)),          # last axis, 16-cell suffix, 640-cell suffix
