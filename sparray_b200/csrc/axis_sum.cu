@@ -287,10 +287,8 @@ __global__ void __launch_bounds__(256) axis_accumulate_lastaxis_kernel(const int
             if (touched) touched[c] = 1;             // a flag per cell: explicit zeros survive
         }
     };
-    for (int64_t base = warp_global * chunk; base < n; base += nwarps * chunk) {
+    auto load_chunk = [&](int64_t base, int64_t (&key)[kAccItems], T (&tv)[kAccItems]) {
         const int64_t i0 = base + (int64_t)lane * kAccItems;
-        int64_t key[kAccItems];
-        T tv[kAccItems];
         if (aligned && base + chunk <= n) {          // (uniform) a full chunk: two 128-bit loads of indices
             Load4<int64_t>::run(idx + i0, key);
             Load4<T>::run(val + i0, tv);
@@ -300,6 +298,22 @@ __global__ void __launch_bounds__(256) axis_accumulate_lastaxis_kernel(const int
                 key[j] = i0 + j < n ? __ldcs(idx + i0 + j) : -1;
                 tv[j] = i0 + j < n ? __ldcs(val + i0 + j) : T(0);
             }
+        }
+    };
+    // the next chunk's loads are issued before the current chunk is worked on
+    int64_t key[kAccItems], nkey[kAccItems];
+    T tv[kAccItems], ntv[kAccItems];
+#ifndef SPB_ACC_PIPE
+#define SPB_ACC_PIPE 1
+#endif
+    int64_t base = warp_global * chunk;
+    if (SPB_ACC_PIPE && base < n) load_chunk(base, key, tv);
+    for (; base < n; base += nwarps * chunk) {
+        const int64_t nbase = base + nwarps * chunk;
+        if (SPB_ACC_PIPE) {
+            if (nbase < n) load_chunk(nbase, nkey, ntv);
+        } else {
+            load_chunk(base, key, tv);
         }
         double v[kAccItems];
 #pragma unroll
@@ -313,7 +327,8 @@ __global__ void __launch_bounds__(256) axis_accumulate_lastaxis_kernel(const int
             for (int j = 3; j > 0; --j)
                 if (key[j] < 0) jl = j - 1;
             const uint64_t g0 = fastdiv((uint64_t)key[0], dv);
-            const uint64_t gl = jl == 0 ? g0 : fastdiv((uint64_t)key[jl], dv);
+            const int64_t kl = key[3] >= 0 ? key[3] : (key[2] >= 0 ? key[2] : (key[1] >= 0 ? key[1] : key[0]));
+            const uint64_t gl = jl == 0 ? g0 : fastdiv((uint64_t)kl, dv);
             if (g0 == gl) {            // one run (all four elements, or the real ones of the last chunk)
                 const uint64_t c = g0 - (uint64_t)cell_lo;
                 if (c < (uint64_t)cells) {
@@ -349,6 +364,13 @@ __global__ void __launch_bounds__(256) axis_accumulate_lastaxis_kernel(const int
         if (cell >= 0 && last) {
             atomicAdd(acc + cell, s);
             if (touched) touched[cell] = 1;
+        }
+        if (SPB_ACC_PIPE) {
+#pragma unroll
+            for (int j = 0; j < kAccItems; ++j) {
+                key[j] = nkey[j];
+                tv[j] = ntv[j];
+            }
         }
     }
 }

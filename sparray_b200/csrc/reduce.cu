@@ -486,14 +486,28 @@ __global__ void __launch_bounds__(256) spmv_runs_kernel(const int64_t* __restric
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t chunk = 32 * kSpmvRun;
-    for (int64_t base = warp_global * chunk; base < n; base += nwarps * chunk) {
+    auto load_chunk = [&](int64_t base, int64_t (&key)[kSpmvRun], T (&v)[kSpmvRun]) {
         const int64_t i0 = base + (int64_t)lane * kSpmvRun;
-        int64_t key[kSpmvRun];
-        T v[kSpmvRun];
 #pragma unroll
         for (int j = 0; j < kSpmvRun; ++j) {
             key[j] = i0 + j < n ? __ldcs(idx + i0 + j) : -1;
             v[j] = i0 + j < n ? __ldcs(val + i0 + j) : T(0);
+        }
+    };
+    // the next chunk's (index, value) loads are in flight while this chunk's x gathers are
+    int64_t key[kSpmvRun], nkey[kSpmvRun];
+    T v[kSpmvRun], nv[kSpmvRun];
+#ifndef SPB_SPMV_PIPE
+#define SPB_SPMV_PIPE 1
+#endif
+    int64_t base = warp_global * chunk;
+    if (SPB_SPMV_PIPE && base < n) load_chunk(base, key, v);
+    for (; base < n; base += nwarps * chunk) {
+        const int64_t nbase = base + nwarps * chunk;
+        if (SPB_SPMV_PIPE) {
+            if (nbase < n) load_chunk(nbase, nkey, nv);
+        } else {
+            load_chunk(base, key, v);
         }
         int64_t row[kSpmvRun];
         double prod[kSpmvRun];
@@ -545,6 +559,13 @@ __global__ void __launch_bounds__(256) spmv_runs_kernel(const int64_t* __restric
         }
         const bool last = lane == 31 || ((heads >> (lane + 1)) & 1u);
         if (cell >= 0 && last) atomicAdd(y + cell, s);
+        if (SPB_SPMV_PIPE) {
+#pragma unroll
+            for (int j = 0; j < kSpmvRun; ++j) {
+                key[j] = nkey[j];
+                v[j] = nv[j];
+            }
+        }
     }
 }
 static_assert(kSpmvRun == 4, "the single-run sum above is written out for 4 elements");
