@@ -76,15 +76,36 @@ __global__ void __launch_bounds__(256) axis_accumulate_kernel(const int64_t* __r
     const int64_t warp_global = gtid >> 5;
     const int64_t nwarps = nthreads >> 5;
     const int64_t chunk = 32 * kAccUnroll;
-    for (int64_t base = warp_global * chunk; base < n; base += nwarps * chunk) {
-        int64_t key[kAccUnroll];
-        double v[kAccUnroll];
+    auto load_chunk = [&](int64_t base, int64_t (&k)[kAccUnroll], T (&t)[kAccUnroll]) {
 #pragma unroll
         for (int u = 0; u < kAccUnroll; ++u) {
             const int64_t i = base + u * 32 + lane;
-            key[u] = i < n ? __ldcs(idx + i) : -1;
-            v[u] = i < n ? (double)__ldcs(val + i) + 0.0 : 0.0;              // (-0.0 goes in as +0.0)
+            k[u] = i < n ? __ldcs(idx + i) : -1;
+            t[u] = i < n ? __ldcs(val + i) : T(0);
         }
+    };
+    // the next chunk's loads are issued before the current chunk's atomics
+#ifndef SPB_ACC_PIPE2
+#define SPB_ACC_PIPE2 1
+#endif
+    int64_t key[kAccUnroll], nkey[kAccUnroll];
+    T tv[kAccUnroll], ntv[kAccUnroll];
+    int64_t base = warp_global * chunk;
+    if (SPB_ACC_PIPE2 && base < n) load_chunk(base, nkey, ntv);
+    for (; base < n; base += nwarps * chunk) {
+        if (SPB_ACC_PIPE2) {
+#pragma unroll
+            for (int u = 0; u < kAccUnroll; ++u) {
+                key[u] = nkey[u];
+                tv[u] = ntv[u];
+            }
+            if (base + nwarps * chunk < n) load_chunk(base + nwarps * chunk, nkey, ntv);
+        } else {
+            load_chunk(base, key, tv);
+        }
+        double v[kAccUnroll];
+#pragma unroll
+        for (int u = 0; u < kAccUnroll; ++u) v[u] = (double)tv[u] + 0.0;     // (-0.0 goes in as +0.0)
 #pragma unroll
         for (int u = 0; u < kAccUnroll; ++u)
             if (key[u] >= 0) key[u] = window_cell(key[u], rk, cell_lo, cells);
