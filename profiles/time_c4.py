@@ -20,6 +20,7 @@ W = sp.FlatSparray(wi, wv, shape=(10 ** 6, 10 ** 6), is_canonical=True)
 x = torch.randn(10 ** 6, device="cuda", dtype=torch.float64)
 xn = x.cpu().numpy()
 print("c4 sum(axis=1) f64 100M: %.0f us" % t(lambda: W.sum(axis=1)))
-print("c4 dot(x)      f64 100M: %.0f us" % t(lambda: W.dot(x)))
+from sparray_b200 import _kernels as k
+print("c4 spmv kernel f64 100M: %.0f us" % t(lambda: k.spmv(wi, wv, 10 ** 6, 10 ** 6, x, torch.float64)))
 W32 = sp.FlatSparray(wi, wv.float(), shape=(10 ** 6, 10 ** 6), is_canonical=True)
 print("c4 sum(axis=1) f32 100M: %.0f us" % t(lambda: W32.sum(axis=1)))

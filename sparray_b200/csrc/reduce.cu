@@ -476,7 +476,10 @@ __global__ void __launch_bounds__(256) spmv_rows_kernel(const int64_t* __restric
 // gathers in flight per lane) and adds up those of its first row; a lane whose elements all lie in one row --
 // the usual case -- hands (row, sum) to ONE segmented shuffle scan per 32 * kSpmvRun elements, a lane that
 // straddles rows adds its pieces atomically on its own.
-constexpr int kSpmvRun = 4;
+#ifndef SPB_SPMV_RUN
+#define SPB_SPMV_RUN 4
+#endif
+constexpr int kSpmvRun = SPB_SPMV_RUN;
 
 template <typename T>
 __global__ void __launch_bounds__(256) spmv_runs_kernel(const int64_t* __restrict__ idx, const T* __restrict__ val,
@@ -529,7 +532,11 @@ __global__ void __launch_bounds__(256) spmv_runs_kernel(const int64_t* __restric
         double s = 0.0;
         if (single) {
             cell = row[0];
-            s = (prod[0] + prod[1]) + (prod[2] + prod[3]);
+#pragma unroll
+            for (int h = 1; h < kSpmvRun; h <<= 1)            // pairwise tree: (p0 + p1) + (p2 + p3) ...
+#pragma unroll
+                for (int j = 0; j + h < kSpmvRun; j += 2 * h) prod[j] += prod[j + h];
+            s = prod[0];
         } else {
             int64_t run = -1;
             double rs = 0.0;
@@ -568,7 +575,7 @@ __global__ void __launch_bounds__(256) spmv_runs_kernel(const int64_t* __restric
         }
     }
 }
-static_assert(kSpmvRun == 4, "the single-run sum above is written out for 4 elements");
+static_assert((kSpmvRun & (kSpmvRun - 1)) == 0, "the single-run sum is a pairwise tree");
 
 template <typename T>
 int launch_spmv_rows(const int64_t* idx, const void* vals, int64_t n, int64_t ncols, int64_t nrows, const void* x,
