@@ -9,13 +9,14 @@ import numpy as np
 _DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN = os.path.join(_DIR, "golden_v1.npz")
 GOLDEN_F = os.path.join(_DIR, "golden_f_v1.npz")      # make_golden_f.py
+GOLDEN_G = os.path.join(_DIR, "golden_g_v1.npz")      # long rows (last-axis sums, dot): make_golden_g.py
 _CACHE = {}
 
 
 def load():
     if "z" not in _CACHE:
         arrays, manifest = {}, []
-        for path in (GOLDEN, GOLDEN_F):
+        for path in (GOLDEN, GOLDEN_F, GOLDEN_G):
             z = np.load(path)
             arrays.update({k: z[k] for k in z.files if k != "manifest"})
             manifest += json.loads(str(z["manifest"]))
